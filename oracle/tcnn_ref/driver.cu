@@ -1,0 +1,202 @@
+// TEST INFRASTRUCTURE ONLY -- driver around the REFERENCE's own NRC arithmetic (tiny-cuda-nn,
+// compiled unmodified from /root/reference/tiny-cuda-nn by oracle/tcnn_ref/Makefile).  It drives tcnn
+// exactly like the reference's en::NeuralRadianceCache does (reference src/NeuralRadianceCache.cu:11-156:
+// same JSON, legacy default stream, inference on EMA weights, training_step + loss() per batch) and
+//   * `dump`  writes tensors that pin the CPU oracle and the product (tests/golden/tcnn_*.npz), and
+//   * `bench` times the reference-equivalent InferAndTrain frame on the GPU ("tcnn on one B200").
+// This file is original glue; it contains no tcnn code.
+#include <tiny-cuda-nn/config.h>
+#include <tiny-cuda-nn/gpu_memory.h>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace tcnn;
+using precision_t = network_precision_t;
+
+static std::map<std::string, std::string> g_args;
+static std::string arg(const std::string& k, const std::string& dflt) { auto it = g_args.find(k); return it == g_args.end() ? dflt : it->second; }
+static long argl(const std::string& k, long d) { return std::stol(arg(k, std::to_string(d))); }
+static double argd(const std::string& k, double d) { return std::stod(arg(k, std::to_string(d))); }
+
+template <typename T> static std::vector<T> read_file(const std::string& path) {
+	std::ifstream f(path, std::ios::binary | std::ios::ate);
+	if (!f) { fprintf(stderr, "cannot open %s\n", path.c_str()); exit(2); }
+	size_t n = f.tellg(); f.seekg(0);
+	std::vector<T> v(n / sizeof(T));
+	f.read((char*)v.data(), n);
+	return v;
+}
+template <typename T> static void write_dev(const std::string& path, const T* dptr, size_t n) {
+	std::vector<T> h(n);
+	CUDA_CHECK_THROW(cudaMemcpy(h.data(), dptr, n * sizeof(T), cudaMemcpyDeviceToHost));
+	std::ofstream f(path, std::ios::binary);
+	f.write((const char*)h.data(), n * sizeof(T));
+}
+
+// Encoding presets: reference src/AppConfig.cpp:16-80
+static json encoding_config(int pos_id, int dir_id) {
+	json pos, dir;
+	switch (pos_id) {
+		case 0: pos = {{"otype", "HashGrid"}, {"n_dims_to_encode", 3}, {"n_levels", 16}, {"n_features_per_level", 2}, {"log2_hashmap_size", 19}, {"base_resolution", 16}, {"per_level_scale", 2.0}}; break;
+		case 1: pos = {{"otype", "Identity"}, {"n_dims_to_encode", 3}}; break;
+		case 2: pos = {{"otype", "TriangleWave"}, {"n_dims_to_encode", 3}, {"n_frequencies", 12}}; break;
+		case 3: pos = {{"otype", "Frequency"}, {"n_dims_to_encode", 3}, {"n_frequencies", 12}}; break;
+		default: fprintf(stderr, "bad pos id\n"); exit(2);
+	}
+	switch (dir_id) {
+		case 0: dir = {{"otype", "OneBlob"}, {"n_dims_to_encode", 2}, {"n_bins", 4}}; break;
+		case 1: dir = {{"otype", "Identity"}, {"n_dims_to_encode", 2}}; break;
+		case 2: dir = {{"otype", "TriangleWave"}, {"n_dims_to_encode", 2}, {"n_frequencies", 4}}; break;
+		default: fprintf(stderr, "bad dir id\n"); exit(2);
+	}
+	return {{"otype", "Composite"}, {"reduction", "Concatenation"}, {"nested", {pos, dir}}};
+}
+
+// reference src/NeuralRadianceCache.cu:16-37
+static json model_config() {
+	return {
+		{"loss", {{"otype", arg("loss", "RelativeL2Luminance")}}},
+		{"optimizer", {{"otype", "EMA"}, {"decay", (float)argd("ema", 0.99)}, {"nested", {{"otype", arg("optimizer", "Adam")}, {"learning_rate", (float)argd("lr", 0.01)}}}}},
+		{"encoding", encoding_config((int)argl("pos", 0), (int)argl("dir", 0))},
+		{"network", {{"otype", "FullyFusedMLP"}, {"activation", "ReLU"}, {"output_activation", "None"}, {"n_neurons", (int)argl("width", 64)}, {"n_hidden_layers", (int)argl("depth", 6)}}},
+	};
+}
+
+// Q6: rows of network_input that tcnn leaves uninitialised read back whatever the arena held.  Zero the
+// arena region first so those rows are deterministic zeros (driver-side only; tcnn itself is untouched).
+static void zero_arena(size_t bytes) {
+	auto a = allocate_workspace(nullptr, bytes);
+	CUDA_CHECK_THROW(cudaMemsetAsync(a.data(), 0, bytes, nullptr));
+}
+
+static int run_dump() {
+	const std::string out = arg("out", "gpurun_out/tcnn_dump");
+	const uint32_t n_infer = (uint32_t)argl("n_infer", 4096), B = (uint32_t)argl("batch", 1024), steps = (uint32_t)argl("steps", 4);
+	const bool zero = argl("zero_arena", 1) != 0;
+	auto infer_in_h = read_file<float>(arg("infer_in", ""));
+	auto train_in_h = read_file<float>(arg("train_in", ""));
+	auto train_tgt_h = read_file<float>(arg("train_tgt", ""));
+	if (infer_in_h.size() < (size_t)n_infer * 5 || train_in_h.size() < (size_t)steps * B * 5 || train_tgt_h.size() < (size_t)steps * B * 3) { fprintf(stderr, "input files too small\n"); return 2; }
+
+	TrainableModel model = create_from_config(5, 3, model_config());
+	const size_t P = model.trainer->n_params();
+	printf("{\"n_params\": %zu, \"padded_input\": %u, \"padded_output\": %u}\n", P, model.network->num_encoded_dims(), model.network->padded_output_width());
+	write_dev(out + "/params_init.f32", model.trainer->params_full_precision(), P);
+
+	GPUMemory<float> infer_in(infer_in_h.size()), infer_out((size_t)n_infer * 3), train_in(train_in_h.size()), train_tgt(train_tgt_h.size());
+	infer_in.copy_from_host(infer_in_h); train_in.copy_from_host(train_in_h); train_tgt.copy_from_host(train_tgt_h);
+	GPUMatrix<float> m_in(infer_in.data(), 5, n_infer), m_out(infer_out.data(), 3, n_infer);
+
+	// (1) reference frame 0: inference on the (all-zero) EMA weights
+	if (zero) zero_arena((size_t)1 << 30);
+	model.network->inference(m_in, m_out);
+	write_dev(out + "/infer_ema_step0.f32", infer_out.data(), (size_t)n_infer * 3);
+	// (2) encoder + network with the WORKING weights (what training sees)
+	{
+		if (zero) zero_arena((size_t)1 << 30);
+		GPUMatrixDynamic<precision_t> net_in(model.network->num_encoded_dims(), n_infer, nullptr, model.network->encoding()->preferred_output_layout());
+		model.network->encoding()->forward(nullptr, m_in, &net_in, false, false);
+		CUDA_CHECK_THROW(cudaDeviceSynchronize());
+		write_dev(out + "/network_input.f16", (const uint16_t*)net_in.data(), (size_t)net_in.m() * net_in.n());
+		printf("{\"network_input_layout\": \"%s\"}\n", net_in.layout() == CM ? "AoS" : "SoA");
+	}
+	if (zero) zero_arena((size_t)1 << 30);
+	model.network->inference(nullptr, m_in, m_out, false);
+	write_dev(out + "/infer_working_step0.f32", infer_out.data(), (size_t)n_infer * 3);
+
+	// (3) training steps exactly like NeuralRadianceCache::Train
+	std::vector<float> losses;
+	for (uint32_t s = 0; s < steps; s++) {
+		GPUMatrix<float> bi(train_in.data() + (size_t)s * B * 5, 5, B), bt(train_tgt.data() + (size_t)s * B * 3, 3, B);
+		if (zero) zero_arena((size_t)1 << 30);
+		auto ctx = model.trainer->training_step(bi, bt);
+		losses.push_back(model.trainer->loss(*ctx));
+		if (s == 0) {
+			CUDA_CHECK_THROW(cudaDeviceSynchronize());
+			write_dev(out + "/grad_step0.f16", (const uint16_t*)model.trainer->param_gradients(), P);
+			write_dev(out + "/output_step0.f16", (const uint16_t*)ctx->output.data(), (size_t)16 * B);
+			write_dev(out + "/dL_doutput_step0.f16", (const uint16_t*)ctx->dL_doutput.data(), (size_t)16 * B);
+			write_dev(out + "/params_step1.f32", model.trainer->params_full_precision(), P);
+			write_dev(out + "/ema_step1.f16", (const uint16_t*)model.trainer->params_inference(), P);
+		}
+	}
+	{ std::ofstream f(out + "/losses.f32", std::ios::binary); f.write((const char*)losses.data(), losses.size() * 4); }
+	write_dev(out + "/params_final.f32", model.trainer->params_full_precision(), P);
+	write_dev(out + "/ema_final.f16", (const uint16_t*)model.trainer->params_inference(), P);
+	if (zero) zero_arena((size_t)1 << 30);
+	model.network->inference(m_in, m_out);
+	write_dev(out + "/infer_ema_final.f32", infer_out.data(), (size_t)n_infer * 3);
+	printf("{\"losses\": [");
+	for (size_t i = 0; i < losses.size(); i++) printf("%s%.9g", i ? ", " : "", losses[i]);
+	printf("]}\n");
+	return 0;
+}
+
+// Reference-equivalent NRC frame: Inference (batches of 2^log2_infer) then Train (reference
+// src/NeuralRadianceCache.cu:97-156), timed with CUDA events on the legacy default stream.
+static int run_bench() {
+	const uint32_t n_infer = (uint32_t)argl("n_infer", 1920 * 1080), B = (uint32_t)argl("batch", 1 << 14), n_batches = (uint32_t)argl("batches", 4);
+	const uint32_t infer_batch = (uint32_t)argl("infer_batch", 1 << 21);
+	const int frames = (int)argl("frames", 100), warmup = (int)argl("warmup", 20);
+	const bool train = argl("train", 1) != 0, infer = argl("infer", 1) != 0;
+	TrainableModel model = create_from_config(5, 3, model_config());
+	GPUMemory<float> infer_in((size_t)n_infer * 5), infer_out((size_t)n_infer * 3), train_in((size_t)n_batches * B * 5), train_tgt((size_t)n_batches * B * 3);
+	{
+		// synthetic records like bench.py: pos ~ U[0,1)^3 + skySize/2 (Q4), theta ~ U[-.5,1.5), phi ~ U[0,1)
+		std::vector<float> h((size_t)n_infer * 5); pcg32 rng{1337};
+		const float off[3] = {31.1585f, 21.1475f, 38.3535f};
+		for (size_t i = 0; i < (size_t)n_infer; i++) { for (int d = 0; d < 3; d++) h[i * 5 + d] = rng.next_float() + off[d]; h[i * 5 + 3] = rng.next_float() * 2 - 0.5f; h[i * 5 + 4] = rng.next_float(); }
+		infer_in.copy_from_host(h);
+		std::vector<float> t((size_t)n_batches * B * 5), g((size_t)n_batches * B * 3);
+		for (size_t i = 0; i < (size_t)n_batches * B; i++) { for (int d = 0; d < 3; d++) t[i * 5 + d] = rng.next_float() + off[d]; t[i * 5 + 3] = rng.next_float() * 2 - 0.5f; t[i * 5 + 4] = rng.next_float(); for (int d = 0; d < 3; d++) g[i * 3 + d] = rng.next_float() * 2; }
+		train_in.copy_from_host(t); train_tgt.copy_from_host(g);
+	}
+	cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+	float loss = 0;
+	auto frame = [&]() {
+		if (infer) for (uint32_t o = 0; o < n_infer; o += infer_batch) {
+			uint32_t n = std::min(infer_batch, n_infer - o);
+			GPUMatrix<float> bi(infer_in.data() + (size_t)o * 5, 5, n), bo(infer_out.data() + (size_t)o * 3, 3, n);
+			model.network->inference(bi, bo);
+		}
+		if (train) for (uint32_t s = 0; s < n_batches; s++) {
+			GPUMatrix<float> bi(train_in.data() + (size_t)s * B * 5, 5, B), bt(train_tgt.data() + (size_t)s * B * 3, 3, B);
+			auto ctx = model.trainer->training_step(bi, bt);
+			loss = model.trainer->loss(*ctx);
+		}
+	};
+	for (int i = 0; i < warmup; i++) frame();
+	CUDA_CHECK_THROW(cudaDeviceSynchronize());
+	cudaEventRecord(e0);
+	for (int i = 0; i < frames; i++) frame();
+	cudaEventRecord(e1); cudaEventSynchronize(e1);
+	float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+	const double per = ms / frames;
+	const double q = (infer ? (double)n_infer : 0.0) + (train ? (double)n_batches * B : 0.0);
+	printf("{\"impl\": \"tcnn\", \"ms_per_frame\": %.6f, \"queries_per_s\": %.6g, \"n_infer\": %u, \"train_batch\": %u, \"train_batches\": %u, \"frames\": %d, \"loss\": %.6g, \"pos\": %ld, \"dir\": %ld, \"depth\": %ld}\n",
+		per, q / (per * 1e-3), infer ? n_infer : 0, B, train ? n_batches : 0, frames, loss, argl("pos", 0), argl("dir", 0), argl("depth", 6));
+	return 0;
+}
+
+int main(int argc, char** argv) {
+	if (argc < 2) { fprintf(stderr, "usage: tcnn_oracle dump|bench key=value ...\n"); return 2; }
+	for (int i = 2; i < argc; i++) {
+		std::string s = argv[i]; auto p = s.find('=');
+		if (p == std::string::npos) { fprintf(stderr, "bad arg %s\n", argv[i]); return 2; }
+		g_args[s.substr(0, p)] = s.substr(p + 1);
+	}
+	try {
+		std::string mode = argv[1];
+		if (mode == "dump") return run_dump();
+		if (mode == "bench") return run_bench();
+		fprintf(stderr, "unknown mode\n");
+		return 2;
+	} catch (const std::exception& e) {
+		fprintf(stderr, "tcnn_oracle: %s\n", e.what());
+		return 1;
+	}
+}
