@@ -1,0 +1,536 @@
+// Host side of the Neural Radiance Cache: en::NeuralRadianceCache re-built on the sm_100a kernels of nrc_kernels.cuh,
+// plus its C ABI (include/nrc_hpm_b200.h).  Mirrors reference src/NeuralRadianceCache.cu:11-178 (ctor / Init /
+// InferAndTrain / Inference / Train / semaphores) and the slice of tiny-cuda-nn's Trainer it drives
+// (trainer.h:50-87 initialisation, :163-211 training_step / loss; network_with_input_encoding.h:115-130 parameter order).
+#include "nrc_host.h"
+#include "nrc_kernels.cuh"
+#include "mini_json.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <random>
+#include <vector>
+
+namespace nrchpm {
+
+std::atomic<uint64_t> g_launch_count{0};
+static thread_local std::string t_last_error;
+void set_last_error(const std::string& msg) { t_last_error = msg; }
+
+// ------------------------------------------------------------------------------------------------ config
+static int parse_pos(const mini_json::Value& v, NrcConfig& c) {
+    const std::string t = v.string("otype", "");
+    if (t == "HashGrid" || t == "Grid") {
+        c.n_levels = (int)v.number("n_levels", 16);
+        c.n_features = (int)v.number("n_features_per_level", 2);
+        c.log2_hashmap_size = (int)v.number("log2_hashmap_size", 19);
+        c.base_resolution = (int)v.number("base_resolution", 16);
+        c.per_level_scale = (float)v.number("per_level_scale", 2.0);
+        return POS_HASHGRID;
+    }
+    if (t == "Identity") return POS_IDENTITY;
+    if (t == "TriangleWave") { c.n_freq_pos = (int)v.number("n_frequencies", 12); return POS_TRIANGLE; }
+    if (t == "Frequency") { c.n_freq_pos = (int)v.number("n_frequencies", 12); return POS_FREQUENCY; }
+    throw Error(NRCHPM_ERR_UNSUPPORTED, "position encoding '" + t + "' is not one of the reference presets (src/AppConfig.cpp:16-48)");
+}
+static int parse_dir(const mini_json::Value& v, NrcConfig& c) {
+    const std::string t = v.string("otype", "");
+    if (t == "OneBlob") { c.n_bins = (int)v.number("n_bins", 4); return DIR_ONEBLOB; }
+    if (t == "Identity") return DIR_IDENTITY;
+    if (t == "TriangleWave") { c.n_freq_dir = (int)v.number("n_frequencies", 4); return DIR_TRIANGLE; }
+    throw Error(NRCHPM_ERR_UNSUPPORTED, "direction encoding '" + t + "' is not one of the reference presets (src/AppConfig.cpp:50-73)");
+}
+
+NrcConfig NrcConfig::from_json(const std::string& text) {
+    NrcConfig c;
+    mini_json::Value j;
+    try { j = mini_json::parse(text); } catch (const std::exception& e) { throw Error(NRCHPM_ERR_INVALID, e.what()); }
+    if (j.has("loss")) {
+        const std::string t = j.at("loss").string("otype", "RelativeL2Luminance");
+        if (t != "RelativeL2Luminance") throw Error(NRCHPM_ERR_UNSUPPORTED, "loss '" + t + "': only RelativeL2Luminance (the reference default, src/main.cu:433) is implemented");
+    }
+    if (j.has("optimizer")) {
+        const auto& o = j.at("optimizer");
+        const mini_json::Value* adam = &o;
+        if (o.string("otype", "") == "EMA") {
+            c.ema_decay = (float)o.number("decay", 0.99);
+            if (o.has("nested")) adam = &o.at("nested");
+        }
+        const std::string t = adam->string("otype", "Adam");
+        if (t != "Adam") throw Error(NRCHPM_ERR_UNSUPPORTED, "optimizer '" + t + "': only EMA(Adam) (src/NeuralRadianceCache.cu:20-27) is implemented");
+        c.learning_rate = (float)adam->number("learning_rate", 1e-3);
+        c.beta1 = (float)adam->number("beta1", 0.9); c.beta2 = (float)adam->number("beta2", 0.999);
+        c.epsilon = (float)adam->number("epsilon", 1e-8); c.l2_reg = (float)adam->number("l2_reg", 1e-8);
+    }
+    NRCHPM_REQUIRE(j.has("encoding"), "config has no 'encoding'");
+    const auto& enc = j.at("encoding");
+    NRCHPM_REQUIRE(enc.string("otype", "") == "Composite" && enc.has("nested") && enc.at("nested").arr.size() == 2,
+                   "encoding must be Composite{nested:[position, direction]} (src/AppConfig.cpp:75-80)");
+    c.pos_enc = parse_pos(enc.at("nested").arr[0], c);
+    c.dir_enc = parse_dir(enc.at("nested").arr[1], c);
+    if (j.has("network")) {
+        const auto& n = j.at("network");
+        c.n_neurons = (int)n.number("n_neurons", 64);
+        c.n_hidden_layers = (int)n.number("n_hidden_layers", 5);
+        const std::string act = n.string("activation", "ReLU"), oact = n.string("output_activation", "None");
+        if (act != "ReLU" || oact != "None") throw Error(NRCHPM_ERR_UNSUPPORTED, "only activation ReLU / output_activation None (src/NeuralRadianceCache.cu:30-36)");
+    }
+    c.infer_batch_size = (uint32_t)j.number("infer_batch_size", (double)(1u << 21));
+    c.train_batch_size = (uint32_t)j.number("train_batch_size", (double)(1u << 14));
+    c.train_batch_count = (uint32_t)j.number("train_batch_count", 4);
+    if (j.has("compat")) c.oneblob_soa_bug = j.at("compat").boolean("oneblob_soa_bug", true);
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------------ derived layout
+static float grid_scale(uint32_t level, float log2_pls, uint32_t base) { return exp2f((float)level * log2_pls) * (float)base - 1.0f; }   // common_device.h:700-706
+static uint32_t grid_resolution(float scale) { return (uint32_t)ceilf(scale) + 1; }                                                       // common_device.h:708-710
+
+void NrcCache::derive() {
+    const NrcConfig& c = cfg_;
+    NRCHPM_REQUIRE(c.n_neurons == 64, "n_neurons must be 64 (tcgen05 tile of this build)");
+    NRCHPM_REQUIRE(c.n_hidden_layers >= 1 && c.n_hidden_layers <= 8, "n_hidden_layers must be in [1, 8]");
+    NRCHPM_REQUIRE(c.n_features == 2, "HashGrid n_features_per_level must be 2");
+    NRCHPM_REQUIRE(c.n_levels >= 1 && c.n_levels <= kMaxLevels, "HashGrid n_levels must be in [1, 16]");
+    NRCHPM_REQUIRE(c.n_freq_pos >= 1 && c.n_freq_pos <= 12 && c.n_freq_dir >= 1 && c.n_freq_dir <= 8 && c.n_bins >= 1 && c.n_bins <= 8, "encoding sizes out of range");
+    EncParams& e = enc_;
+    std::memset(&e, 0, sizeof(e));
+    e.pos_enc = c.pos_enc; e.dir_enc = c.dir_enc;
+    e.n_levels = c.n_levels; e.n_freq_pos = c.n_freq_pos; e.n_freq_dir = c.n_freq_dir; e.n_bins = c.n_bins;
+    const int pw[4] = {c.n_levels * 2, 3, 3 * c.n_freq_pos, 3 * c.n_freq_pos * 2};
+    const int dw[3] = {2 * c.n_bins, 2, 2 * c.n_freq_dir};
+    e.pos_w = pw[c.pos_enc]; e.dir_w = dw[c.dir_enc];
+    e.dir_off = e.pos_w;
+    e.in_w = ((e.pos_w + e.dir_w + 15) / 16) * 16;                      // set_alignment(16), network_with_input_encoding.h:47
+    NRCHPM_REQUIRE(e.in_w <= 80, "encoded width > 80 not supported");
+    e.oneblob_soa = (c.pos_enc == POS_HASHGRID) ? 1 : 0;                // composite.h:400-403
+    e.soa_bug = (e.oneblob_soa && c.dir_enc == DIR_ONEBLOB && c.oneblob_soa_bug) ? 1 : 0;
+    n_grid_ = 0;
+    if (c.pos_enc == POS_HASHGRID) {                                    // grid.h:699-724
+        uint32_t offset = 0;
+        const float log2_pls = std::log2(c.per_level_scale);
+        for (int i = 0; i < c.n_levels; i++) {
+            const float scale = grid_scale(i, log2_pls, c.base_resolution);
+            const uint32_t res = grid_resolution(scale);
+            const uint32_t max_params = 0xFFFFFFFFu / 2;
+            uint32_t p = std::pow((float)res, 3) > (float)max_params ? max_params : res * res * res;
+            p = ((p + 7) / 8) * 8;
+            p = std::min(p, 1u << c.log2_hashmap_size);
+            e.level_scale[i] = scale;
+            e.level_hsize[i] = p;
+            e.level_offset[i] = offset;
+            // grid_index (common_device.h:668-690) with its uint32 stride arithmetic, including the wrap-around for res >= 2^16
+            uint32_t stride = 1, s[3] = {0, 0, 0};
+            for (uint32_t dim = 0; dim < 3 && stride <= p; ++dim) { s[dim] = stride; stride *= res; }
+            e.level_s0[i] = s[0]; e.level_s1[i] = s[1]; e.level_s2[i] = s[2];
+            e.level_hash[i] = p < stride ? 1u : 0u;
+            offset += p;
+        }
+        n_grid_ = (size_t)offset * 2;
+    }
+    const int W = c.n_neurons;
+    n_mlp_ = (size_t)W * e.in_w + (size_t)(c.n_hidden_layers - 1) * W * W + (size_t)kOutPad * W;
+    n_params_ = n_mlp_ + n_grid_;
+}
+
+// pcg32 as vendored by tiny-cuda-nn (dependencies/pcg32/pcg32.h)
+namespace {
+struct Pcg32 {
+    uint64_t state, inc;
+    explicit Pcg32(uint64_t initstate, uint64_t initseq = 1u) { state = 0u; inc = (initseq << 1u) | 1u; next_uint(); state += initstate; next_uint(); }
+    uint32_t next_uint() {
+        uint64_t old = state;
+        state = old * 0x5851f42d4c957f2dULL + inc;
+        uint32_t xorshifted = (uint32_t)(((old >> 18u) ^ old) >> 27u);
+        uint32_t rot = (uint32_t)(old >> 59u);
+        return (xorshifted >> rot) | (xorshifted << ((~rot + 1u) & 31));
+    }
+    float next_float() { uint32_t u = (next_uint() >> 9) | 0x3f800000u; float f; std::memcpy(&f, &u, 4); return f - 1.0f; }
+};
+}  // namespace
+
+// Trainer::initialize_params (trainer.h:68-87): MLP xavier-uniform matrix by matrix on the host (gpu_matrix.h:284-299,
+// fully_fused_mlp.cu:866-891), grid U(-1e-4, 1e-4) with the device generator's element order (random.h:40-66).
+void NrcCache::init_params(uint64_t seed) {
+    std::vector<float> master(n_params_);
+    std::seed_seq seq{(uint32_t)seed};
+    std::vector<uint32_t> seeds(2);
+    seq.generate(seeds.begin(), seeds.end());
+    Pcg32 rng{seeds.front()};
+    const int W = cfg_.n_neurons, H = cfg_.n_hidden_layers;
+    size_t off = 0;
+    auto fill = [&](int rows, int cols) {
+        const float scale = std::sqrt(6.0f / (float)(cols + rows));
+        for (size_t i = 0; i < (size_t)rows * cols; i++) master[off + i] = rng.next_float() * 2.0f * scale - scale;
+        off += (size_t)rows * cols;
+    };
+    fill(W, enc_.in_w);
+    for (int i = 0; i < H - 1; i++) fill(W, W);
+    fill(kOutPad, W);
+    if (n_grid_) {
+        const size_t n = n_grid_;
+        const size_t n_threads = 128 * ((((n + 3) / 4) + 127) / 128);
+        float* g = master.data() + n_mlp_;
+        Pcg32 base = rng;
+        for (size_t i = 0; i < n_threads; i++) {
+            Pcg32 r = base;
+            for (int j = 0; j < 4; j++) {
+                const size_t idx = i + n_threads * j;
+                const float v = r.next_float();
+                if (idx < n) g[idx] = fmaf(v, 2e-4f, -1e-4f);
+            }
+            base.next_uint(); base.next_uint(); base.next_uint(); base.next_uint();
+        }
+    }
+    set_params_fp32(master.data());
+    NRCHPM_CUDA(cudaMemset(ema16_.ptr, 0, ema16_.bytes()));             // ema.h:93-94
+    NRCHPM_CUDA(cudaMemset(m1_.ptr, 0, m1_.bytes()));
+    NRCHPM_CUDA(cudaMemset(m2_.ptr, 0, m2_.bytes()));
+    NRCHPM_CUDA(cudaMemset(steps_.ptr, 0, steps_.bytes()));
+    NRCHPM_CUDA(cudaMemset(grad16_.ptr, 0, grad16_.bytes()));
+    current_step_ = 0;
+}
+
+NrcCache::NrcCache(const NrcConfig& cfg, uint64_t seed) : cfg_(cfg) {
+    derive();
+    int dev = 0;
+    NRCHPM_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    NRCHPM_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) throw Error(NRCHPM_ERR_CUDA, std::string("this library contains sm_100a code only; device is ") + prop.name);
+    sm_count_ = prop.multiProcessorCount;
+    master_.allocate(n_params_); w16_.allocate(n_params_); ema16_.allocate(n_params_); grad16_.allocate(n_params_);
+    m1_.allocate(n_params_); m2_.allocate(n_params_); steps_.allocate(n_params_);
+    loss_dev_.allocate(1);
+    NRCHPM_CUDA(cudaMemset(loss_dev_.ptr, 0, sizeof(float)));
+    init_params(seed);
+    setup_kernels();
+}
+
+NrcCache::~NrcCache() {}
+
+void NrcCache::set_params_fp32(const float* host_master) {
+    NRCHPM_CUDA(cudaMemcpy(master_.ptr, host_master, n_params_ * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<__half> h(n_params_);
+    for (size_t i = 0; i < n_params_; i++) h[i] = __float2half_rn(host_master[i]);
+    NRCHPM_CUDA(cudaMemcpy(w16_.ptr, h.data(), n_params_ * sizeof(__half), cudaMemcpyHostToDevice));
+}
+
+void NrcCache::set_ema(const float* host_ema) {
+    std::vector<__half> h(n_params_);
+    for (size_t i = 0; i < n_params_; i++) h[i] = __float2half_rn(host_ema[i]);
+    NRCHPM_CUDA(cudaMemcpy(ema16_.ptr, h.data(), n_params_ * sizeof(__half), cudaMemcpyHostToDevice));
+}
+
+void NrcCache::get_params(int which, float* out) {
+    if (which == 3 && grads_pending_) {       // before the optimizer ran, the MLP gradient only exists as per-chunk partials
+        const float* src = dw_source_ ? dw_source_ : dw_partials_.ptr;
+        nrc_partials_to_half_kernel<<<(unsigned)((n_mlp_ + 255) / 256), 256, 0, stream_>>>(src, dw_source_ ? 1u : dw_chunks_, (uint32_t)n_mlp_, grad16_.ptr);
+        check_launch("nrc_partials_to_half_kernel");
+    }
+    NRCHPM_CUDA(cudaDeviceSynchronize());
+    if (which == 0 || which == 4 || which == 5) {
+        const float* src = which == 0 ? master_.ptr : which == 4 ? m1_.ptr : m2_.ptr;
+        NRCHPM_CUDA(cudaMemcpy(out, src, n_params_ * sizeof(float), cudaMemcpyDeviceToHost));
+    } else if (which >= 1 && which <= 3) {
+        std::vector<__half> h(n_params_);
+        const __half* src = which == 1 ? w16_.ptr : which == 2 ? ema16_.ptr : grad16_.ptr;
+        NRCHPM_CUDA(cudaMemcpy(h.data(), src, n_params_ * sizeof(__half), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n_params_; i++) out[i] = __half2float(h[i]);
+    } else if (which == 6) {
+        std::vector<uint32_t> h(n_params_);
+        NRCHPM_CUDA(cudaMemcpy(h.data(), steps_.ptr, n_params_ * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n_params_; i++) out[i] = (float)h[i];
+    } else throw Error(NRCHPM_ERR_INVALID, "nrc_get_params: which must be 0..6");
+}
+
+// ------------------------------------------------------------------------------------------------ kernel dispatch
+#define NRC_DISPATCH_INW(inw, ...)                                                         \
+    switch (inw) {                                                                         \
+        case 16: { constexpr int IN_W = 16; __VA_ARGS__; } break;                          \
+        case 32: { constexpr int IN_W = 32; __VA_ARGS__; } break;                          \
+        case 48: { constexpr int IN_W = 48; __VA_ARGS__; } break;                          \
+        case 64: { constexpr int IN_W = 64; __VA_ARGS__; } break;                          \
+        case 80: { constexpr int IN_W = 80; __VA_ARGS__; } break;                          \
+        default: throw Error(NRCHPM_ERR_UNSUPPORTED, "unsupported encoded width");         \
+    }
+
+void NrcCache::setup_kernels() {
+    const int H = cfg_.n_hidden_layers;
+    NRC_DISPATCH_INW(enc_.in_w, {
+        NRCHPM_CUDA(cudaFuncSetAttribute(nrc_forward_kernel<IN_W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem_bytes<IN_W>(H)));
+        NRCHPM_CUDA(cudaFuncSetAttribute(nrc_forward_kernel<IN_W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem_bytes<IN_W>(H)));
+        NRCHPM_CUDA(cudaFuncSetAttribute(nrc_backward_kernel<IN_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem_bytes<IN_W>(H)));
+        NRCHPM_CUDA(cudaFuncSetAttribute(nrc_dw_kernel<IN_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDwSmemBytes));
+    });
+}
+
+void NrcCache::encode(const float* d_in, uint32_t n, bool use_ema, void* d_out_half, cudaStream_t s) {
+    if (n == 0) return;
+    nrc_encode_kernel<<<(n + 127) / 128, 128, 0, s>>>(enc_, use_ema ? ema16_.ptr : w16_.ptr, (uint32_t)n_mlp_, d_in, n, (__half*)d_out_half);
+    check_launch("nrc_encode_kernel");
+}
+
+void NrcCache::inference(const float* d_in, float* d_out, uint32_t n, bool use_ema, const uint32_t* d_indices, const uint32_t* d_count, cudaStream_t s) {
+    if (n == 0) return;
+    FwdArgs a{};
+    a.enc = enc_; a.params = use_ema ? ema16_.ptr : w16_.ptr; a.n_mlp = (uint32_t)n_mlp_; a.n_hidden = cfg_.n_hidden_layers;
+    a.in = d_in; a.indices = d_indices; a.d_count = d_count; a.n = n; a.out = d_out;
+    const uint32_t tiles = (n + kTile - 1) / kTile;
+    const uint32_t grid = std::min<uint32_t>((tiles + 1) / 2, (uint32_t)sm_count_ * 2);
+    NRC_DISPATCH_INW(enc_.in_w, {
+        nrc_forward_kernel<IN_W, false><<<grid, kFwdThreads, fwd_smem_bytes<IN_W>(cfg_.n_hidden_layers), s>>>(a);
+    });
+    check_launch("nrc_forward_kernel<infer>");
+}
+
+void NrcCache::ensure_train_scratch(uint32_t B) {
+    if (B <= scratch_batch_) return;
+    const int H = cfg_.n_hidden_layers;
+    x16_.allocate((size_t)B * enc_.in_w);
+    acts_.allocate((size_t)H * B * kWidth);
+    dacts_.allocate((size_t)H * B * kWidth);
+    out16_.allocate((size_t)B * kOutPad);
+    dout16_.allocate((size_t)B * kOutPad);
+    dx16_.allocate((size_t)B * enc_.in_w);
+    loss_partials_.allocate(B / kTile);
+    dw_partials_.allocate((size_t)kMaxDwChunks * n_mlp_);
+    scratch_batch_ = B;
+}
+
+void NrcCache::training_step(const float* d_in, const float* d_target, uint32_t B, bool run_optimizer, cudaStream_t s) {
+    NRCHPM_REQUIRE(B > 0 && B % kTile == 0, "training batch must be a positive multiple of 128 (tcnn: 256, common.h:235)");
+    ensure_train_scratch(B);
+    const int H = cfg_.n_hidden_layers;
+    if (grid_grad_dirty_ && n_grid_) NRCHPM_CUDA(cudaMemsetAsync(grad16_.ptr + n_mlp_, 0, n_grid_ * sizeof(__half), s));   // grid.h:857-860
+    const uint32_t tiles = B / kTile;
+    const uint32_t grid = std::min<uint32_t>((tiles + 1) / 2, (uint32_t)sm_count_ * 2);
+    {
+        FwdArgs a{};
+        a.enc = enc_; a.params = w16_.ptr; a.n_mlp = (uint32_t)n_mlp_; a.n_hidden = H;
+        a.in = d_in; a.n = B; a.target = d_target;
+        a.x16 = x16_.ptr; a.acts = acts_.ptr; a.out16 = out16_.ptr; a.dout16 = dout16_.ptr; a.loss_partials = loss_partials_.ptr;
+        a.loss_scale = cfg_.loss_scale;
+        NRC_DISPATCH_INW(enc_.in_w, { nrc_forward_kernel<IN_W, true><<<grid, kFwdThreads, fwd_smem_bytes<IN_W>(H), s>>>(a); });
+        check_launch("nrc_forward_kernel<train>");
+    }
+    {
+        BwdArgs a{};
+        a.enc = enc_; a.params = w16_.ptr; a.n_mlp = (uint32_t)n_mlp_; a.n_hidden = H; a.n = B;
+        a.in = d_in; a.acts = acts_.ptr; a.dout16 = dout16_.ptr; a.dacts = dacts_.ptr;
+        a.need_dx = n_grid_ ? 1 : 0;
+        a.dx16 = (n_grid_ && keep_dx_) ? dx16_.ptr : nullptr;
+        a.grid_grad = n_grid_ ? grad16_.ptr + n_mlp_ : nullptr;
+        a.loss_partials = loss_partials_.ptr; a.loss_out = loss_dev_.ptr; a.n_loss_partials = tiles;
+        NRC_DISPATCH_INW(enc_.in_w, { nrc_backward_kernel<IN_W><<<grid, kFwdThreads, bwd_smem_bytes<IN_W>(H), s>>>(a); });
+        check_launch("nrc_backward_kernel");
+        grid_grad_dirty_ = n_grid_ != 0;
+    }
+    {
+        DwArgs a{};
+        a.n_hidden = H; a.n = B; a.n_mlp = (uint32_t)n_mlp_;
+        const uint32_t tiles_per_chunk = (tiles + kMaxDwChunks - 1) / kMaxDwChunks;
+        a.kc = tiles_per_chunk * kTile;
+        dw_chunks_ = (B + a.kc - 1) / a.kc;
+        a.x16 = x16_.ptr; a.acts = acts_.ptr; a.dacts = dacts_.ptr; a.dout16 = dout16_.ptr; a.partials = dw_partials_.ptr;
+        NRC_DISPATCH_INW(enc_.in_w, { nrc_dw_kernel<IN_W><<<dim3(dw_chunks_, H + 1), 128, kDwSmemBytes, s>>>(a); });
+        check_launch("nrc_dw_kernel");
+    }
+    last_batch_ = B;
+    dw_source_ = nullptr;
+    loss_valid_ = false;
+    grads_pending_ = true;
+    if (run_optimizer) optimizer_step(s);
+}
+
+void NrcCache::optimizer_step(cudaStream_t s) {
+    NRCHPM_REQUIRE(grads_pending_, "nrc_optimizer_step without a preceding training step");
+    current_step_++;
+    OptArgs a{};
+    a.n_params = n_params_; a.n_mlp = n_mlp_;
+    a.master = master_.ptr; a.w16 = w16_.ptr; a.ema16 = ema16_.ptr; a.grad16 = grad16_.ptr; a.m1 = m1_.ptr; a.m2 = m2_.ptr; a.steps = steps_.ptr;
+    a.partials = dw_source_ ? dw_source_ : dw_partials_.ptr; a.n_chunks = dw_source_ ? 1u : dw_chunks_;
+    a.lr = cfg_.learning_rate; a.beta1 = cfg_.beta1; a.beta2 = cfg_.beta2; a.eps = cfg_.epsilon; a.l2_reg = cfg_.l2_reg; a.loss_scale = cfg_.loss_scale;
+    a.ema_decay = cfg_.ema_decay;
+    a.ema_debias_old = 1 - (float)std::pow(cfg_.ema_decay, current_step_ - 1);          // ema.h:105-108
+    a.ema_debias_new = 1.0f / (1 - (float)std::pow(cfg_.ema_decay, current_step_));
+    nrc_optimizer_kernel<<<(unsigned)((n_params_ + 255) / 256), 256, 0, s>>>(a);
+    check_launch("nrc_optimizer_kernel");
+    grid_grad_dirty_ = false;       // the optimizer re-zeroes every encoding gradient it consumed
+    grads_pending_ = false;
+}
+
+float NrcCache::loss() {
+    if (!loss_valid_) {
+        NRCHPM_CUDA(cudaMemcpyAsync(&loss_host_, loss_dev_.ptr, sizeof(float), cudaMemcpyDeviceToHost, stream_));
+        NRCHPM_CUDA(cudaStreamSynchronize(stream_));
+        loss_valid_ = true;
+    }
+    return loss_host_;
+}
+
+void NrcCache::last_step_tensor(int which, float* host_out) {
+    NRCHPM_REQUIRE(last_batch_ > 0, "no training step has run");
+    NRCHPM_CUDA(cudaDeviceSynchronize());
+    const __half* src; size_t n;
+    if (which == 0) { src = out16_.ptr; n = (size_t)last_batch_ * kOutPad; }
+    else if (which == 1) { src = dout16_.ptr; n = (size_t)last_batch_ * kOutPad; }
+    else if (which == 2) { NRCHPM_REQUIRE(n_grid_ && keep_dx_, "dL/dinput is only kept for encodings with parameters"); src = dx16_.ptr; n = (size_t)last_batch_ * enc_.in_w; }
+    else throw Error(NRCHPM_ERR_INVALID, "nrc_last_step_tensor: which must be 0..2");
+    std::vector<__half> h(n);
+    NRCHPM_CUDA(cudaMemcpy(h.data(), src, n * sizeof(__half), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; i++) host_out[i] = __half2float(h[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ reference-level API
+void NrcCache::init(uint32_t infer_count, float* in, float* out, float* train_in, float* train_target, cudaExternalSemaphore_t start,
+                    cudaExternalSemaphore_t finished, cudaStream_t stream) {
+    // src/NeuralRadianceCache.cu:52: inferCount % 16 == 0
+    NRCHPM_REQUIRE(infer_count % 16 == 0, "NRC requires inferCount to be a multiple of 16");
+    NRCHPM_REQUIRE(cfg_.train_batch_size % kTile == 0, "train batch size must be a multiple of 128");
+    infer_count_ = infer_count; infer_in_ = in; infer_out_ = out; train_in_ = train_in; train_target_ = train_target;
+    start_sem_ = start; finished_sem_ = finished; stream_ = stream;
+    // src/NeuralRadianceCache.cu:66-80: floor(N/B) full batches + one remainder batch
+    infer_batches_.clear();
+    const uint32_t B = cfg_.infer_batch_size;
+    for (uint32_t o = 0; o < infer_count; o += B) infer_batches_.push_back({o, std::min(B, infer_count - o)});
+    ensure_train_scratch(cfg_.train_batch_size);
+    initialised_ = true;
+}
+
+void NrcCache::run_inference(const uint32_t* filter_host) {
+    for (size_t i = 0; i < infer_batches_.size(); i++) {
+        if (filter_host && filter_host[i] == 0) continue;                        // src/NeuralRadianceCache.cu:136-144
+        const auto& b = infer_batches_[i];
+        inference(infer_in_ + 5 * (size_t)b.first, infer_out_ + 3 * (size_t)b.first, b.second, true, nullptr, nullptr, stream_);
+    }
+}
+
+void NrcCache::run_train() {
+    const uint32_t B = cfg_.train_batch_size;
+    for (uint32_t i = 0; i < cfg_.train_batch_count; i++)                        // src/NeuralRadianceCache.cu:147-156
+        training_step(train_in_ + 5 * (size_t)i * B, train_target_ + 3 * (size_t)i * B, B, true, stream_);
+}
+
+void NrcCache::wait_start() {
+    if (!start_sem_) return;
+    cudaExternalSemaphoreWaitParams p{};
+    NRCHPM_CUDA(cudaWaitExternalSemaphoresAsync(&start_sem_, &p, 1, stream_));   // src/NeuralRadianceCache.cu:158-167
+}
+void NrcCache::signal_finished() {
+    if (!finished_sem_) return;
+    cudaExternalSemaphoreSignalParams p{};
+    NRCHPM_CUDA(cudaSignalExternalSemaphoresAsync(&finished_sem_, &p, 1, stream_));   // :169-178
+}
+
+void NrcCache::infer_and_train(const uint32_t* filter_host, bool train) {
+    NRCHPM_REQUIRE(initialised_, "nrc_init has not been called");
+    wait_start();
+    run_inference(filter_host);
+    if (train) run_train();
+    signal_finished();
+}
+
+}  // namespace nrchpm
+
+// ================================================================================================ C ABI
+using namespace nrchpm;
+
+extern "C" {
+
+const char* nrchpm_last_error(void) { return t_last_error.c_str(); }
+int nrchpm_version(void) { return 100; }
+uint64_t nrchpm_launch_count(void) { return g_launch_count.load(); }
+
+int nrc_create(const char* config_json, uint64_t seed, nrc_cache** out) {
+    return guard([&] {
+        NRCHPM_REQUIRE(config_json && out, "nrc_create: null argument");
+        *out = nullptr;
+        NrcConfig c = NrcConfig::from_json(config_json);
+        *out = new nrc_cache(c, seed);
+    });
+}
+int nrc_destroy(nrc_cache* c) { return guard([&] { delete c; }); }
+int nrc_init(nrc_cache* c, uint32_t infer_count, float* in, float* out, float* tin, float* ttgt, void* s0, void* s1, void* stream) {
+    return guard([&] {
+        NRCHPM_REQUIRE(c, "null cache");
+        c->impl.init(infer_count, in, out, tin, ttgt, (cudaExternalSemaphore_t)s0, (cudaExternalSemaphore_t)s1, (cudaStream_t)stream);
+    });
+}
+int nrc_infer_and_train(nrc_cache* c, const uint32_t* f, int train) { return guard([&] { NRCHPM_REQUIRE(c, "null cache"); c->impl.infer_and_train(f, train != 0); }); }
+int nrc_inference(nrc_cache* c, const uint32_t* f) {
+    return guard([&] { NRCHPM_REQUIRE(c && c->impl.initialised(), "nrc_init has not been called"); c->impl.wait_start(); c->impl.run_inference(f); c->impl.signal_finished(); });
+}
+int nrc_train(nrc_cache* c) {
+    return guard([&] { NRCHPM_REQUIRE(c && c->impl.initialised(), "nrc_init has not been called"); c->impl.wait_start(); c->impl.run_train(); c->impl.signal_finished(); });
+}
+int nrc_get_loss(nrc_cache* c, float* loss) { return guard([&] { NRCHPM_REQUIRE(c && loss, "null argument"); *loss = c->impl.loss(); }); }
+size_t nrc_get_infer_batch_count(const nrc_cache* c) { return c ? c->impl.infer_batch_count() : 0; }
+size_t nrc_get_train_batch_count(const nrc_cache* c) { return c ? c->impl.config().train_batch_count : 0; }
+uint32_t nrc_get_infer_batch_size(const nrc_cache* c) { return c ? c->impl.config().infer_batch_size : 0; }
+uint32_t nrc_get_train_batch_size(const nrc_cache* c) { return c ? c->impl.config().train_batch_size : 0; }
+uint64_t nrc_n_params(const nrc_cache* c) { return c ? c->impl.n_params() : 0; }
+uint64_t nrc_n_mlp_params(const nrc_cache* c) { return c ? c->impl.n_mlp() : 0; }
+uint32_t nrc_input_width(const nrc_cache* c) { return c ? (uint32_t)c->impl.enc().in_w : 0; }
+int nrc_get_params(nrc_cache* c, int which, float* out) { return guard([&] { NRCHPM_REQUIRE(c && out, "null argument"); c->impl.get_params(which, out); }); }
+int nrc_set_params_fp32(nrc_cache* c, const float* m) { return guard([&] { NRCHPM_REQUIRE(c && m, "null argument"); c->impl.set_params_fp32(m); }); }
+int nrc_set_ema(nrc_cache* c, const float* m) { return guard([&] { NRCHPM_REQUIRE(c && m, "null argument"); c->impl.set_ema(m); }); }
+int nrc_gradient_buffers(nrc_cache* c, float** mlp, void** enc) {
+    return guard([&] { NRCHPM_REQUIRE(c, "null cache"); c->impl.gradient_buffers(mlp, enc); });
+}
+int nrc_encode_batch(nrc_cache* c, const float* d_in, uint32_t n, int use_ema, void* d_out, void* stream) {
+    return guard([&] { NRCHPM_REQUIRE(c && d_in && d_out, "null argument"); c->impl.encode(d_in, n, use_ema != 0, d_out, (cudaStream_t)stream); });
+}
+int nrc_inference_batch(nrc_cache* c, const float* d_in, float* d_out, uint32_t n, int use_ema, void* stream) {
+    return guard([&] { NRCHPM_REQUIRE(c && d_in && d_out, "null argument"); c->impl.inference(d_in, d_out, n, use_ema != 0, nullptr, nullptr, (cudaStream_t)stream); });
+}
+int nrc_inference_indexed(nrc_cache* c, const float* d_in, float* d_out, const uint32_t* idx, const uint32_t* cnt, uint32_t max_n, int use_ema, void* stream) {
+    return guard([&] { NRCHPM_REQUIRE(c && d_in && d_out && idx, "null argument"); c->impl.inference(d_in, d_out, max_n, use_ema != 0, idx, cnt, (cudaStream_t)stream); });
+}
+int nrc_training_step(nrc_cache* c, const float* d_in, const float* d_tgt, uint32_t batch, int run_opt, void* stream) {
+    return guard([&] { NRCHPM_REQUIRE(c && d_in && d_tgt, "null argument"); c->impl.set_stream_for_loss((cudaStream_t)stream); c->impl.training_step(d_in, d_tgt, batch, run_opt != 0, (cudaStream_t)stream); });
+}
+int nrc_optimizer_step(nrc_cache* c, void* stream) { return guard([&] { NRCHPM_REQUIRE(c, "null cache"); c->impl.optimizer_step((cudaStream_t)stream); }); }
+int nrc_last_step_tensor(nrc_cache* c, int which, float* out) { return guard([&] { NRCHPM_REQUIRE(c && out, "null argument"); c->impl.last_step_tensor(which, out); }); }
+
+int nrc_inference_host(nrc_cache* c, const float* h_in, float* h_out, uint32_t n, int use_ema) {
+    return guard([&] { NRCHPM_REQUIRE(c && h_in && h_out, "null argument"); c->impl.inference_host(h_in, h_out, n, use_ema != 0); });
+}
+int nrc_training_step_host(nrc_cache* c, const float* h_in, const float* h_tgt, uint32_t batch, float* loss_out) {
+    return guard([&] { NRCHPM_REQUIRE(c && h_in && h_tgt, "null argument"); c->impl.training_step_host(h_in, h_tgt, batch, loss_out); });
+}
+
+}  // extern "C"
+
+namespace nrchpm {
+// Data-parallel training: collapse the per-chunk weight-gradient partials into one fp32 buffer that the caller can
+// all-reduce (together with the fp16 encoding gradient) before nrc_optimizer_step consumes both.
+void NrcCache::gradient_buffers(float** mlp, void** enc) {
+    NRCHPM_REQUIRE(grads_pending_, "nrc_gradient_buffers: call nrc_training_step(run_optimizer=0) first");
+    if (!dw_source_) {
+        mlp_grad_f32_.ensure(n_mlp_);
+        nrc_reduce_partials_kernel<<<(unsigned)((n_mlp_ + 255) / 256), 256, 0, stream_>>>(dw_partials_.ptr, dw_chunks_, (uint32_t)n_mlp_, mlp_grad_f32_.ptr);
+        check_launch("nrc_reduce_partials_kernel");
+        dw_source_ = mlp_grad_f32_.ptr;
+    }
+    if (mlp) *mlp = mlp_grad_f32_.ptr;
+    if (enc) *enc = n_grid_ ? (void*)(grad16_.ptr + n_mlp_) : nullptr;
+}
+void NrcCache::inference_host(const float* h_in, float* h_out, uint32_t n, bool use_ema) {
+    host_in_.ensure((size_t)n * 5); host_out_.ensure((size_t)n * 3);
+    cudaStream_t s = stream_;
+    NRCHPM_CUDA(cudaMemcpyAsync(host_in_.ptr, h_in, (size_t)n * 5 * sizeof(float), cudaMemcpyHostToDevice, s));
+    inference(host_in_.ptr, host_out_.ptr, n, use_ema, nullptr, nullptr, s);
+    NRCHPM_CUDA(cudaMemcpyAsync(h_out, host_out_.ptr, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    NRCHPM_CUDA(cudaStreamSynchronize(s));
+}
+void NrcCache::training_step_host(const float* h_in, const float* h_tgt, uint32_t B, float* loss_out) {
+    host_in_.ensure((size_t)B * 5); host_tgt_.ensure((size_t)B * 3);
+    cudaStream_t s = stream_;
+    NRCHPM_CUDA(cudaMemcpyAsync(host_in_.ptr, h_in, (size_t)B * 5 * sizeof(float), cudaMemcpyHostToDevice, s));
+    NRCHPM_CUDA(cudaMemcpyAsync(host_tgt_.ptr, h_tgt, (size_t)B * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    training_step(host_in_.ptr, host_tgt_.ptr, B, true, s);
+    if (loss_out) *loss_out = loss();
+}
+}  // namespace nrchpm

@@ -1,0 +1,98 @@
+// nrchpm::NrcCache -- host object behind the nrc_* C ABI; the B200-native counterpart of en::NeuralRadianceCache
+// (reference include/engine/graphics/NeuralRadianceCache.hpp:10-64) fused with the tcnn::Trainer state it owns
+// (tiny-cuda-nn/include/tiny-cuda-nn/trainer.h:322-336: fp32 master, fp16 working weights, fp16 gradients;
+// optimizers/adam.h, optimizers/ema.h state).
+#pragma once
+#include <cuda_fp16.h>
+#include <string>
+#include <utility>
+#include <vector>
+#include "common.h"
+#include "nrc_types.h"
+
+namespace nrchpm {
+
+struct NrcConfig {
+    int pos_enc = 0, dir_enc = 0;                 // src/AppConfig.cpp:16-73 presets
+    int n_neurons = 64, n_hidden_layers = 5;
+    bool oneblob_soa_bug = true;
+    int n_levels = 16, n_features = 2, log2_hashmap_size = 19, base_resolution = 16;
+    float per_level_scale = 2.0f;
+    int n_freq_pos = 12, n_freq_dir = 4, n_bins = 4;
+    float learning_rate = 1e-3f, ema_decay = 0.99f, beta1 = 0.9f, beta2 = 0.999f, epsilon = 1e-8f, l2_reg = 1e-8f;   // adam.h:313-317
+    float loss_scale = 128.0f;                    // common.h:232 (fp16 network precision)
+    uint32_t infer_batch_size = 1u << 21, train_batch_size = 1u << 14, train_batch_count = 4;
+    static NrcConfig from_json(const std::string& text);
+};
+
+constexpr uint32_t kMaxDwChunks = 32;
+
+class NrcCache {
+public:
+    NrcCache(const NrcConfig& cfg, uint64_t seed);
+    ~NrcCache();
+    const NrcConfig& config() const { return cfg_; }
+    const EncParams& enc() const { return enc_; }
+    uint64_t n_params() const { return n_params_; }
+    uint64_t n_mlp() const { return n_mlp_; }
+    bool initialised() const { return initialised_; }
+    size_t infer_batch_count() const { return infer_batches_.size(); }
+
+    void init(uint32_t infer_count, float* in, float* out, float* train_in, float* train_target, cudaExternalSemaphore_t start,
+              cudaExternalSemaphore_t finished, cudaStream_t stream);
+    void infer_and_train(const uint32_t* filter_host, bool train);
+    void run_inference(const uint32_t* filter_host);
+    void run_train();
+    void wait_start();
+    void signal_finished();
+    float loss();
+
+    void encode(const float* d_in, uint32_t n, bool use_ema, void* d_out_half, cudaStream_t s);
+    void inference(const float* d_in, float* d_out, uint32_t n, bool use_ema, const uint32_t* d_indices, const uint32_t* d_count, cudaStream_t s);
+    void training_step(const float* d_in, const float* d_target, uint32_t B, bool run_optimizer, cudaStream_t s);
+    void optimizer_step(cudaStream_t s);
+    void inference_host(const float* h_in, float* h_out, uint32_t n, bool use_ema);
+    void training_step_host(const float* h_in, const float* h_tgt, uint32_t B, float* loss_out);
+    void set_stream_for_loss(cudaStream_t s) { if (!initialised_) stream_ = s; }
+
+    void get_params(int which, float* out);
+    void set_params_fp32(const float* host_master);
+    void set_ema(const float* host_ema);
+    void gradient_buffers(float** mlp, void** enc);
+    void last_step_tensor(int which, float* host_out);
+    void keep_dx(bool k) { keep_dx_ = k; }
+    cudaStream_t stream() const { return stream_; }
+
+private:
+    void derive();
+    void init_params(uint64_t seed);
+    void setup_kernels();
+    void ensure_train_scratch(uint32_t B);
+
+    NrcConfig cfg_;
+    EncParams enc_;
+    size_t n_mlp_ = 0, n_grid_ = 0, n_params_ = 0;
+    int sm_count_ = 148;
+    DeviceBuffer<float> master_, m1_, m2_, loss_dev_, loss_partials_, dw_partials_, mlp_grad_f32_;
+    DeviceBuffer<__half> w16_, ema16_, grad16_, x16_, acts_, dacts_, out16_, dout16_, dx16_;
+    DeviceBuffer<uint32_t> steps_;
+    DeviceBuffer<float> host_in_, host_out_, host_tgt_;
+    uint32_t scratch_batch_ = 0, last_batch_ = 0, dw_chunks_ = 0, current_step_ = 0;
+    const float* dw_source_ = nullptr;
+    bool grid_grad_dirty_ = false, grads_pending_ = false, keep_dx_ = true, loss_valid_ = true, initialised_ = false;
+    float loss_host_ = 0;
+    // en::NeuralRadianceCache::Init state
+    uint32_t infer_count_ = 0;
+    float *infer_in_ = nullptr, *infer_out_ = nullptr, *train_in_ = nullptr, *train_target_ = nullptr;
+    cudaExternalSemaphore_t start_sem_ = nullptr, finished_sem_ = nullptr;
+    cudaStream_t stream_ = nullptr;
+    std::vector<std::pair<uint32_t, uint32_t>> infer_batches_;   // (first record, count)
+};
+
+}  // namespace nrchpm
+
+// the opaque handle of the C ABI
+struct nrc_cache {
+    nrchpm::NrcCache impl;
+    nrc_cache(const nrchpm::NrcConfig& c, uint64_t seed) : impl(c, seed) {}
+};

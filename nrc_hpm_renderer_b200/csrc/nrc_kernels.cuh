@@ -1,0 +1,714 @@
+// sm_100a kernels of the Neural Radiance Cache: input encodings, fully fused MLP forward (inference and training),
+// loss, fused backward (+ hash-grid gradient scatter), weight gradients, Adam + EMA.
+//
+// What they replace in the reference (all in the tiny-cuda-nn submodule, paths relative to tiny-cuda-nn/):
+//   include/tiny-cuda-nn/encodings/grid.h:49-212 (kernel_grid), :215-320 (kernel_grid_backward)
+//   include/tiny-cuda-nn/encodings/oneblob.h:85-127, triangle_wave.h:46-82, frequency.h:46-80, identity.h:46-66
+//   src/fully_fused_mlp.cu:499-557 (kernel_mlp_fused), :150-259 (kernel_mlp_fused_backward), :783-836 (weight / input
+//   gradient GEMMs through CUTLASS), include/tiny-cuda-nn/common_device.h:990-999 (trim_and_cast)
+//   include/tiny-cuda-nn/losses/relative_l2_luminance.h:40-88, optimizers/adam.h:48-121, optimizers/ema.h:63-76
+//
+// Design (B200-first, not a translation): one warpgroup (128 threads) owns a tile of 128 records, one record per
+// thread == one TMEM lane.  The activations never leave the SM: layer 0 reads the encoded inputs from shared memory
+// (tcgen05.mma SS), every later layer takes its A operand from TMEM (tcgen05.mma TS) where the previous epilogue
+// (tcgen05.ld -> ReLU -> fp16 -> tcgen05.st) left it.  All weight matrices stay resident in shared memory in the
+// canonical no-swizzle UMMA layout (K-major for forward, MN-major for backward, so the row-major fp16 parameter
+// vector is copied in 16-byte chunks without any transpose).  fp32 accumulation in TMEM (tcnn accumulates in fp16).
+#pragma once
+#include <cuda_fp16.h>
+#include <cstdint>
+#include "tc05.cuh"
+#include "nrc_types.h"
+
+namespace nrchpm {
+
+// ---------------------------------------------------------------------------------------------- encodings
+__device__ __forceinline__ float quartic_cdf(float x, float inv_radius) {      // common_device.h:905-920
+    const float u = x * inv_radius;
+    const float u2 = u * u;
+    const float u4 = u2 * u2;
+    return fmaxf(0.0f, fminf(1.0f, ((float)15 / 16) * u * (1 - ((float)2 / 3) * u2 + ((float)1 / 5) * u4) + 0.5f));
+}
+
+struct GridLevel {
+    uint32_t idx[8];
+    float w[8];
+};
+
+// grid.h:49-212 / common_device.h:632-718, 842-868: cell corners (entry indices relative to the level) and weights
+__device__ __forceinline__ void grid_level_cell(const EncParams& e, int l, float x0, float x1, float x2, GridLevel& c) {
+    const float scale = e.level_scale[l];
+    float p[3] = {fmaf(scale, x0, 0.5f), fmaf(scale, x1, 0.5f), fmaf(scale, x2, 0.5f)};
+    uint32_t g[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const float t = floorf(p[d]);
+        g[d] = (uint32_t)(int)t;
+        p[d] -= t;
+    }
+    const uint32_t hs = e.level_hsize[l], s0 = e.level_s0[l], s1 = e.level_s1[l], s2 = e.level_s2[l];
+    const bool hashed = e.level_hash[l] != 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        float w = 1;
+        uint32_t q[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            if ((k & (1 << d)) == 0) { w *= 1 - p[d]; q[d] = g[d]; } else { w *= p[d]; q[d] = g[d] + 1; }
+        }
+        uint32_t index = hashed ? ((q[0] * 1u) ^ (q[1] * 2654435761u) ^ (q[2] * 805459861u)) : (q[0] * s0 + q[1] * s1 + q[2] * s2);
+        c.idx[k] = index % hs;
+        c.w[k] = w;
+    }
+}
+
+// put(k, half) / put2(k_even, half2) receive feature k of this record.
+template <class Put>
+__device__ __forceinline__ void encode_record(const EncParams& e, const __half2* __restrict__ grid, float x0, float x1, float x2,
+                                              float th, float ph, Put& put) {
+    const __half one = __float2half_rn(1.0f);
+    // ---- position
+    if (e.pos_enc == POS_HASHGRID) {
+#pragma unroll 2
+        for (int l = 0; l < e.n_levels; l++) {
+            GridLevel c;
+            grid_level_cell(e, l, x0, x1, x2, c);
+            const __half2* base = grid + e.level_offset[l];
+            __half2 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = base[c.idx[k]];
+            __half2 r = __float2half2_rn(0.0f);
+#pragma unroll
+            for (int k = 0; k < 8; k++) r = __hfma2(__half2half2(__float2half_rn(c.w[k])), v[k], r);   // grid.h:144-163: fp16 fma
+            put.put2(2 * l, r);
+        }
+    } else if (e.pos_enc == POS_IDENTITY) {
+        put.put(0, __float2half_rn(x0)); put.put(1, __float2half_rn(x1)); put.put(2, __float2half_rn(x2));
+    } else if (e.pos_enc == POS_TRIANGLE) {
+        const float xs[3] = {x0, x1, x2};
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+            for (int f = 0; f < e.n_freq_pos; f++) {
+                const float x = scalbnf(xs[d], f - 1);
+                const float val = x + (float)f * 0.25f;
+                put.put(d * e.n_freq_pos + f, __float2half_rn(fabsf(val - floorf(val) - 0.5f) * 4 - 1));
+            }
+    } else {
+        const float xs[3] = {x0, x1, x2};
+        const float PI = 3.14159265358979323846f;
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+            for (int f = 0; f < e.n_freq_pos; f++) {
+                const float x = scalbnf(xs[d], f) * PI;
+                put.put((d * e.n_freq_pos + f) * 2 + 0, __float2half_rn(__sinf(x)));
+                put.put((d * e.n_freq_pos + f) * 2 + 1, __float2half_rn(__sinf(x + PI / 2)));
+            }
+    }
+    // ---- direction
+    const int o = e.dir_off;
+    const float ds[2] = {th, ph};
+    if (e.dir_enc == DIR_ONEBLOB) {
+        const float nb = (float)e.n_bins;
+#pragma unroll
+        for (int d = 0; d < 2; d++) {
+            const float x = ds[d];
+            if (e.oneblob_soa) {                                                               // oneblob.h:99-127
+                float left = quartic_cdf(-x, nb) + quartic_cdf(-x - 1.0f, nb) + quartic_cdf(-x + 1.0f, nb);
+                for (int k = 0; k < e.n_bins; k++) {
+                    const float rb = (float)(k + 1) / nb;
+                    const float right = quartic_cdf(rb - x, nb) + quartic_cdf(rb - x - 1.0f, nb) + quartic_cdf(rb - x + 1.0f, nb);
+                    put.put(o + d * e.n_bins + k, __float2half_rn(right - left));
+                    left = right;
+                }
+            } else {                                                                           // oneblob.h:46-70, 85-97
+                const float first = quartic_cdf(-x, nb) + quartic_cdf(-x - 1.0f, nb) + quartic_cdf(-x + 1.0f, nb);
+                float left = first;
+                for (int k = 0; k < e.n_bins; k++) {
+                    float right;
+                    if (k == e.n_bins - 1) right = first + 1;
+                    else { const float rb = (float)(k + 1) / nb; right = quartic_cdf(rb - x, nb) + quartic_cdf(rb - x - 1.0f, nb) + quartic_cdf(rb - x + 1.0f, nb); }
+                    put.put(o + d * e.n_bins + k, __float2half_rn(right - left));
+                    left = right;
+                }
+            }
+        }
+    } else if (e.dir_enc == DIR_IDENTITY) {
+        put.put(o + 0, __float2half_rn(th)); put.put(o + 1, __float2half_rn(ph));
+    } else {
+#pragma unroll
+        for (int d = 0; d < 2; d++)
+            for (int f = 0; f < e.n_freq_dir; f++) {
+                const float x = scalbnf(ds[d], f - 1);
+                const float val = x + (float)f * 0.25f;
+                put.put(o + d * e.n_freq_dir + f, __float2half_rn(fabsf(val - floorf(val) - 0.5f) * 4 - 1));
+            }
+    }
+    // ---- padding (composite.h:137-218 pads with 1; SoA OneBlob writes the pad to the wrong rows, Q6)
+    const int first_pad = o + e.dir_w;
+    if (e.soa_bug) {
+        const int n_pad = e.in_w - first_pad;
+        for (int k = first_pad; k < e.in_w; k++) put.put(k, __float2half_rn(0.0f));
+        for (int k = o + 2; k < o + 2 + n_pad; k++) put.put(k, one);
+    } else {
+        for (int k = first_pad; k < e.in_w; k++) put.put(k, one);
+    }
+}
+
+// K-major canonical (no swizzle) tile in shared memory: this thread's row
+struct SmemRowPut {
+    uint8_t* row;   // tile + (r/8)*SBO + (r%8)*16
+    __device__ __forceinline__ void put(int k, __half v) { *reinterpret_cast<__half*>(row + (k >> 3) * 128 + (k & 7) * 2) = v; }
+    __device__ __forceinline__ void put2(int k, __half2 v) { *reinterpret_cast<__half2*>(row + (k >> 3) * 128 + (k & 7) * 2) = v; }
+};
+struct GlobalRowPut {
+    __half* row;
+    __device__ __forceinline__ void put(int k, __half v) { row[k] = v; }
+    __device__ __forceinline__ void put2(int k, __half2 v) { *reinterpret_cast<__half2*>(row + k) = v; }
+};
+
+__global__ void __launch_bounds__(128) nrc_encode_kernel(const __grid_constant__ EncParams e, const __half* __restrict__ params, uint32_t n_mlp,
+                                                         const float* __restrict__ in, uint32_t n, __half* __restrict__ out) {
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n) return;
+    const float* rec = in + 5 * (size_t)i;
+    GlobalRowPut put{out + (size_t)i * e.in_w};
+    encode_record(e, reinterpret_cast<const __half2*>(params + n_mlp), rec[0], rec[1], rec[2], rec[3], rec[4], put);
+}
+
+// ---------------------------------------------------------------------------------------------- helpers
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// row-major [rows][K] fp16 matrix -> K-major canonical tile (B operand of the forward MMAs)
+__device__ __forceinline__ void copy_weights_kmajor(uint8_t* dst, const __half* __restrict__ src, int rows, int K, int tid, int nthreads) {
+    const int k8n = K >> 3, chunks = rows * k8n;
+    for (int c = tid; c < chunks; c += nthreads) {
+        const int n = c / k8n, k8 = c - n * k8n;
+        *reinterpret_cast<int4*>(dst + (n >> 3) * (k8n * 128) + k8 * 128 + (n & 7) * 16) = *reinterpret_cast<const int4*>(src + (size_t)n * K + k8 * 8);
+    }
+}
+// row-major [O][I] fp16 matrix used as B[n=i][k=o] -> MN-major canonical tile (backward MMAs; no transpose needed)
+__device__ __forceinline__ void copy_weights_mnmajor(uint8_t* dst, const __half* __restrict__ src, int O, int I, int tid, int nthreads) {
+    const int i8n = I >> 3, chunks = O * i8n;
+    const int sbo = (O >> 3) * 128;
+    for (int c = tid; c < chunks; c += nthreads) {
+        const int o = c / i8n, i8 = c - o * i8n;
+        *reinterpret_cast<int4*>(dst + i8 * sbo + (o & 7) * 16 + (o >> 3) * 128) = *reinterpret_cast<const int4*>(src + (size_t)o * I + i8 * 8);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- forward
+struct FwdArgs {
+    EncParams enc;
+    const __half* params;       // fp16 parameter vector [network | encoding]: EMA weights for Inference(), working weights for training
+    uint32_t n_mlp;
+    int n_hidden;
+    const float* in;            // records float[*][5]
+    const uint32_t* indices;    // optional compaction list
+    const uint32_t* d_count;    // optional device-side record count (<= n)
+    uint32_t n;
+    float* out;                 // inference: float[*][3]
+    // training only
+    const float* target;        // float[n][3]
+    __half* x16;                // [n][IN_W]   network input
+    __half* acts;               // [H][n][64]  post-ReLU activations
+    __half* out16;              // [n][16]
+    __half* dout16;             // [n][16]     dL/doutput * loss_scale
+    float* loss_partials;       // [n/128]
+    float loss_scale;
+};
+
+constexpr uint32_t kColD = 0, kColA = 96, kColsPerWg = 128;
+
+template <int IN_W>
+__host__ __device__ constexpr size_t fwd_smem_bytes(int n_hidden) {
+    return (size_t)IN_W * 128 + (size_t)(n_hidden - 1) * 8192 + 2048 + 2 * (size_t)IN_W * 256;
+}
+
+template <int IN_W, bool TRAIN>
+__global__ void __launch_bounds__(kFwdThreads, 2) nrc_forward_kernel(const __grid_constant__ FwdArgs a) {
+    using namespace tc05;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t mbar[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float loss_red[2][4];
+    const int tid = threadIdx.x, wg = tid >> 7, r = tid & 127, warp = tid >> 5, lane = tid & 31;
+    const int H = a.n_hidden;
+    uint8_t* w0_s = smem;
+    uint8_t* wh_s = w0_s + IN_W * 128;
+    uint8_t* wo_s = wh_s + (H - 1) * 8192;
+    uint8_t* x_s = wo_s + 2048 + wg * (IN_W * 256);
+
+    if (warp == 0) { tmem_alloc(&tmem_base_s, 2 * kColsPerWg); tmem_relinquish(); }
+    if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); fence_mbar_init(); }
+    copy_weights_kmajor(w0_s, a.params, kWidth, IN_W, tid, kFwdThreads);
+    for (int l = 1; l < H; l++) copy_weights_kmajor(wh_s + (l - 1) * 8192, a.params + IN_W * kWidth + (l - 1) * kWidth * kWidth, kWidth, kWidth, tid, kFwdThreads);
+    copy_weights_kmajor(wo_s, a.params + IN_W * kWidth + (H - 1) * kWidth * kWidth, kOutPad, kWidth, tid, kFwdThreads);
+    fence_proxy_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+
+    const uint32_t tD = tmem_base_s + wg * kColsPerWg + kColD, tA = tmem_base_s + wg * kColsPerWg + kColA;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t idesc64 = make_idesc_f16(128, 64), idesc16 = make_idesc_f16(128, 16);
+    const uint32_t x_addr = smem_u32(x_s), w0_addr = smem_u32(w0_s), wh_addr = smem_u32(wh_s), wo_addr = smem_u32(wo_s);
+    const __half2* grid = reinterpret_cast<const __half2*>(a.params + a.n_mlp);
+    uint64_t* bar = &mbar[wg];
+    uint32_t phase = 0;
+
+    uint32_t n = a.n;
+    if (a.d_count) n = min(n, *a.d_count);
+    const uint32_t n_tiles = (n + kTile - 1) / kTile;
+
+    for (uint32_t tile = blockIdx.x * 2 + wg; tile < n_tiles; tile += gridDim.x * 2) {
+        const uint32_t row = tile * kTile + r;
+        const bool valid = row < n;
+        uint32_t rec = 0;
+        float x0 = 0, x1 = 0, x2 = 0, th = 0, ph = 0;
+        if (valid) {
+            rec = a.indices ? a.indices[row] : row;
+            const float* p = a.in + 5 * (size_t)rec;
+            x0 = p[0]; x1 = p[1]; x2 = p[2]; th = p[3]; ph = p[4];
+        }
+        uint8_t* my_row = x_s + (r >> 3) * (IN_W * 16) + (r & 7) * 16;
+        SmemRowPut put{my_row};
+        encode_record(a.enc, grid, x0, x1, x2, th, ph, put);
+        fence_proxy_async_smem();
+        fence_before();
+        named_bar_sync(1 + wg, 128);
+        if (r == 0) {
+            fence_after();
+#pragma unroll
+            for (int s = 0; s < IN_W / 16; s++)
+                mma_f16_ss(tD, make_smem_desc(x_addr + s * 256, 128, IN_W * 16), make_smem_desc(w0_addr + s * 256, 128, IN_W * 16), idesc64, s > 0);
+            mma_commit(bar);
+        }
+        if (TRAIN) {
+            int4* dst = reinterpret_cast<int4*>(a.x16 + (size_t)row * IN_W);
+#pragma unroll
+            for (int c = 0; c < IN_W / 8; c++) dst[c] = *reinterpret_cast<const int4*>(my_row + c * 128);
+        }
+        mbar_wait(bar, phase); phase ^= 1;
+        fence_after();
+
+        for (int l = 0; l < H; l++) {
+            // epilogue of hidden layer l: ReLU -> fp16 -> A operand of the next layer
+#pragma unroll
+            for (int hf = 0; hf < 2; hf++) {
+                uint32_t acc[32], p[16];
+                tmem_ld32(tD + lane_base + hf * 32, acc);
+                wait_ld();
+                if (l == 0) {
+                    // tcnn's ReLU is max(x, 0) in fp16, which maps NaN to 0 (NaN features reach layer 0 through the
+                    // reference's phi = acos(>1)); cvt.relu would keep the NaN.  Later layers cannot see one.
+                    const __half2 zero2 = __float2half2_rn(0.0f);
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        uint32_t v = pack_f16x2(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
+                        __half2 m = __hmax2(*reinterpret_cast<__half2*>(&v), zero2);
+                        p[j] = *reinterpret_cast<uint32_t*>(&m);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) p[j] = pack_relu_f16x2(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
+                }
+                tmem_st16(tA + lane_base + hf * 16, p);
+                if (TRAIN) {
+                    int4* dst = reinterpret_cast<int4*>(a.acts + ((size_t)l * a.n + row) * kWidth + hf * 32);
+#pragma unroll
+                    for (int c = 0; c < 4; c++) dst[c] = make_int4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
+                }
+            }
+            wait_st();
+            fence_before();
+            named_bar_sync(1 + wg, 128);
+            if (r == 0) {
+                fence_after();
+                if (l < H - 1) {
+#pragma unroll
+                    for (int s = 0; s < 4; s++) mma_f16_ts(tD, tA + s * 8, make_smem_desc(wh_addr + l * 8192 + s * 256, 128, 1024), idesc64, s > 0);
+                } else {
+#pragma unroll
+                    for (int s = 0; s < 4; s++) mma_f16_ts(tD, tA + s * 8, make_smem_desc(wo_addr + s * 256, 128, 1024), idesc16, s > 0);
+                }
+                mma_commit(bar);
+            }
+            mbar_wait(bar, phase); phase ^= 1;
+            fence_after();
+        }
+        // output layer: fp16 like tcnn's network output, then float (common_device.h:990-999)
+        uint32_t o[16];
+        tmem_ld16(tD + lane_base, o);
+        wait_ld();
+        if (!TRAIN) {
+            if (valid) {
+                float* dst = a.out + 3 * (size_t)rec;
+#pragma unroll
+                for (int k = 0; k < 3; k++) dst[k] = __half2float(__float2half_rn(__uint_as_float(o[k])));
+            }
+        } else {
+            uint32_t ph16[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) ph16[j] = pack_f16x2(__uint_as_float(o[2 * j]), __uint_as_float(o[2 * j + 1]));
+            int4* od = reinterpret_cast<int4*>(a.out16 + (size_t)row * kOutPad);
+            od[0] = make_int4(ph16[0], ph16[1], ph16[2], ph16[3]);
+            od[1] = make_int4(ph16[4], ph16[5], ph16[6], ph16[7]);
+            // RelativeL2Luminance (relative_l2_luminance.h:40-88); n_total = batch * 3 (padded dims contribute nothing)
+            float pr[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) pr[k] = __half2float(__float2half_rn(__uint_as_float(o[k])));
+            const float n_total = (float)(a.n * 3u);
+            const float lum = 0.299f * pr[0] + 0.587f * pr[1] + 0.114f * pr[2];
+            const float denom = lum * lum + 0.01f;
+            float loss = 0;
+            uint32_t g16[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) g16[j] = 0;
+            float gk[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float diff = pr[k] - a.target[3 * (size_t)row + k];
+                loss += diff * diff / denom / n_total;
+                gk[k] = a.loss_scale * (2 * diff / denom) / n_total;
+            }
+            g16[0] = pack_f16x2(gk[0], gk[1]);
+            g16[1] = pack_f16x2(gk[2], 0.0f);
+            int4* gd = reinterpret_cast<int4*>(a.dout16 + (size_t)row * kOutPad);
+            gd[0] = make_int4(g16[0], g16[1], 0, 0);
+            gd[1] = make_int4(0, 0, 0, 0);
+            // deterministic per-tile loss sum: warp shuffle tree, then 4 partials added in order
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, s);
+            if (lane == 0) loss_red[wg][warp & 3] = loss;
+            named_bar_sync(1 + wg, 128);
+            if (r == 0) a.loss_partials[tile] = ((loss_red[wg][0] + loss_red[wg][1]) + loss_red[wg][2]) + loss_red[wg][3];
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base_s, 2 * kColsPerWg);
+}
+
+// ---------------------------------------------------------------------------------------------- backward
+struct BwdArgs {
+    EncParams enc;
+    const __half* params;       // working weights
+    uint32_t n_mlp;
+    int n_hidden;
+    uint32_t n;
+    const float* in;            // records (hash-grid scatter recomputes the cells)
+    const __half* acts;         // [H][n][64]
+    const __half* dout16;       // [n][16]
+    __half* dacts;              // [H][n][64] gradients w.r.t. the hidden pre-activations (ReLU mask applied)
+    __half* dx16;               // [n][IN_W] or null
+    __half* grid_grad;          // fp16 gradient of the encoding parameters or null
+    const float* loss_partials;
+    float* loss_out;
+    uint32_t n_loss_partials;
+    int need_dx;
+};
+
+template <int IN_W>
+__host__ __device__ constexpr size_t bwd_smem_bytes(int n_hidden) {
+    return (size_t)IN_W * 128 + (size_t)(n_hidden - 1) * 8192 + 2048;
+}
+
+template <int IN_W>
+__global__ void __launch_bounds__(kFwdThreads, 2) nrc_backward_kernel(const __grid_constant__ BwdArgs a) {
+    using namespace tc05;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t mbar[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, wg = tid >> 7, r = tid & 127, warp = tid >> 5;
+    const int H = a.n_hidden;
+    uint8_t* w0_s = smem;
+    uint8_t* wh_s = w0_s + IN_W * 128;
+    uint8_t* wo_s = wh_s + (H - 1) * 8192;
+
+    if (warp == 0) { tmem_alloc(&tmem_base_s, 2 * kColsPerWg); tmem_relinquish(); }
+    if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); fence_mbar_init(); }
+    if (blockIdx.x == 0 && tid == 0 && a.loss_out) {     // Trainer::loss (trainer.h:205-207): fixed-order sum of the tile partials
+        float s = 0;
+        for (uint32_t i = 0; i < a.n_loss_partials; i++) s += a.loss_partials[i];
+        *a.loss_out = s;
+    }
+    copy_weights_mnmajor(w0_s, a.params, kWidth, IN_W, tid, kFwdThreads);
+    for (int l = 1; l < H; l++) copy_weights_mnmajor(wh_s + (l - 1) * 8192, a.params + IN_W * kWidth + (l - 1) * kWidth * kWidth, kWidth, kWidth, tid, kFwdThreads);
+    copy_weights_mnmajor(wo_s, a.params + IN_W * kWidth + (H - 1) * kWidth * kWidth, kOutPad, kWidth, tid, kFwdThreads);
+    fence_proxy_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+
+    const uint32_t tD = tmem_base_s + wg * kColsPerWg + kColD, tA = tmem_base_s + wg * kColsPerWg + kColA;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t idesc64 = make_idesc_f16(128, 64, 0, 1), idescx = make_idesc_f16(128, IN_W, 0, 1);
+    const uint32_t w0_addr = smem_u32(w0_s), wh_addr = smem_u32(wh_s), wo_addr = smem_u32(wo_s);
+    uint64_t* bar = &mbar[wg];
+    uint32_t phase = 0;
+    const uint32_t n_tiles = a.n / kTile;
+
+    for (uint32_t tile = blockIdx.x * 2 + wg; tile < n_tiles; tile += gridDim.x * 2) {
+        const uint32_t row = tile * kTile + r;
+        {   // dL/doutput row -> A operand (K = 16)
+            const int4* src = reinterpret_cast<const int4*>(a.dout16 + (size_t)row * kOutPad);
+            const int4 v0 = src[0], v1 = src[1];
+            uint32_t p[8] = {(uint32_t)v0.x, (uint32_t)v0.y, (uint32_t)v0.z, (uint32_t)v0.w, (uint32_t)v1.x, (uint32_t)v1.y, (uint32_t)v1.z, (uint32_t)v1.w};
+            tmem_st8(tA + lane_base, p);
+        }
+        wait_st();
+        fence_before();
+        named_bar_sync(1 + wg, 128);
+        if (r == 0) {
+            fence_after();
+            mma_f16_ts(tD, tA, make_smem_desc(wo_addr, 128, 256), idesc64, 0);
+            mma_commit(bar);
+        }
+        mbar_wait(bar, phase); phase ^= 1;
+        fence_after();
+
+        for (int l = H - 1; l >= 0; l--) {
+            const int4* ap = reinterpret_cast<const int4*>(a.acts + ((size_t)l * a.n + row) * kWidth);
+            int4* dp = reinterpret_cast<int4*>(a.dacts + ((size_t)l * a.n + row) * kWidth);
+#pragma unroll
+            for (int hf = 0; hf < 2; hf++) {
+                uint32_t acc[32], p[16];
+                int4 av[4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) av[c] = ap[hf * 4 + c];
+                tmem_ld32(tD + lane_base + hf * 32, acc);
+                wait_ld();
+                const uint32_t* aw = reinterpret_cast<const uint32_t*>(av);
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const float lo = (aw[j] & 0x0000ffffu) ? __uint_as_float(acc[2 * j]) : 0.0f;
+                    const float hi = (aw[j] & 0xffff0000u) ? __uint_as_float(acc[2 * j + 1]) : 0.0f;
+                    p[j] = pack_f16x2(lo, hi);
+                }
+                tmem_st16(tA + lane_base + hf * 16, p);
+#pragma unroll
+                for (int c = 0; c < 4; c++) dp[hf * 4 + c] = make_int4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
+            }
+            if (l == 0 && !a.need_dx) break;
+            wait_st();
+            fence_before();
+            named_bar_sync(1 + wg, 128);
+            if (r == 0) {
+                fence_after();
+                if (l > 0) {
+#pragma unroll
+                    for (int s = 0; s < 4; s++) mma_f16_ts(tD, tA + s * 8, make_smem_desc(wh_addr + (l - 1) * 8192 + s * 256, 128, 1024), idesc64, s > 0);
+                } else {
+#pragma unroll
+                    for (int s = 0; s < 4; s++) mma_f16_ts(tD, tA + s * 8, make_smem_desc(w0_addr + s * 256, 128, 1024), idescx, s > 0);
+                }
+                mma_commit(bar);
+            }
+            mbar_wait(bar, phase); phase ^= 1;
+            fence_after();
+        }
+        if (a.need_dx) {
+            // dL/d(network input): fp16 like tcnn's fc_multiply output (fully_fused_mlp.cu:832-835)
+            uint32_t acc[32];
+            tmem_ld32(tD + lane_base, acc);
+            wait_ld();
+            if (a.dx16) {
+                uint32_t* dst = reinterpret_cast<uint32_t*>(a.dx16 + (size_t)row * IN_W);
+#pragma unroll
+                for (int j = 0; j < 16; j++) dst[j] = pack_f16x2(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
+#pragma unroll
+                for (int c = 32; c < IN_W; c += 16) {
+                    uint32_t t[16];
+                    tmem_ld16(tD + lane_base + c, t);
+                    wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 8; j++) dst[c / 2 + j] = pack_f16x2(__uint_as_float(t[2 * j]), __uint_as_float(t[2 * j + 1]));
+                }
+            }
+            if (a.grid_grad && a.enc.pos_enc == POS_HASHGRID) {
+                // kernel_grid_backward (grid.h:215-320): (half)weight * grad, fp16x2 atomics
+                const float* rp = a.in + 5 * (size_t)row;
+                const float x0 = rp[0], x1 = rp[1], x2 = rp[2];
+                __half2* gg = reinterpret_cast<__half2*>(a.grid_grad);
+#pragma unroll
+                for (int l = 0; l < kMaxLevels; l++) {
+                    if (l >= a.enc.n_levels) break;
+                    uint32_t gp = pack_f16x2(__uint_as_float(acc[2 * l]), __uint_as_float(acc[2 * l + 1]));
+                    const __half2 g = *reinterpret_cast<__half2*>(&gp);
+                    GridLevel c;
+                    grid_level_cell(a.enc, l, x0, x1, x2, c);
+                    __half2* base = gg + a.enc.level_offset[l];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) atomicAdd(base + c.idx[k], __hmul2(__half2half2(__float2half_rn(c.w[k])), g));
+                }
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base_s, 2 * kColsPerWg);
+}
+
+// ---------------------------------------------------------------------------------------------- weight gradients
+// dW_m = sum over the batch of dY_m^T * A_{m-1}: batch is the contraction dimension, both operands are "MN-major"
+// ([sample][feature] rows copied as they are).  blockIdx.x = batch chunk, blockIdx.y = weight matrix.  Each CTA writes
+// its fp32 partial; the optimizer kernel adds the chunks in a fixed order (deterministic, no atomics).
+struct DwArgs {
+    int n_hidden;
+    uint32_t n, kc, n_mlp;
+    const __half* x16;
+    const __half* acts;
+    const __half* dacts;
+    const __half* dout16;
+    float* partials;            // [n_chunks][n_mlp]
+};
+
+constexpr size_t kDwSmemBytes = 2 * (16384 + 20480);
+
+template <int IN_W>
+__global__ void __launch_bounds__(128, 1) nrc_dw_kernel(const __grid_constant__ DwArgs a) {
+    using namespace tc05;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t mbar[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int H = a.n_hidden, m = blockIdx.y;
+    // operands of matrix m: A-op (M = 64 rows of D), B-op (N columns of D)
+    const __half* aop; const __half* bop; int aw, bw;
+    if (m == 0) { aop = a.dacts; aw = kWidth; bop = a.x16; bw = IN_W; }
+    else if (m < H) { aop = a.dacts + (size_t)m * a.n * kWidth; aw = kWidth; bop = a.acts + (size_t)(m - 1) * a.n * kWidth; bw = kWidth; }
+    else { aop = a.acts + (size_t)(H - 1) * a.n * kWidth; aw = kWidth; bop = a.dout16; bw = kOutPad; }
+
+    if (warp == 0) { tmem_alloc(&tmem_base_s, 128); tmem_relinquish(); }
+    if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); fence_mbar_init(); }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tD = tmem_base_s;
+    const uint32_t idesc = make_idesc_f16(64, (uint32_t)bw, 1, 1);
+    const uint32_t b0 = blockIdx.x * a.kc, b1 = min(a.n, b0 + a.kc);
+    uint32_t phase[2] = {0, 0};
+    int it = 0;
+    for (uint32_t b = b0; b < b1; b += kTile, it++) {
+        const int buf = it & 1;
+        uint8_t* as = smem + buf * (16384 + 20480);
+        uint8_t* bs = as + 16384;
+        if (it >= 2) { mbar_wait(&mbar[buf], phase[buf]); phase[buf] ^= 1; }     // MMAs that read this buffer are done
+        // thread = sample: 16-byte chunks land conflict-free at (mn8)*2048 + (b%8)*16 + (b/8)*128
+        const uint32_t off = (tid & 7) * 16 + (tid >> 3) * 128;
+        const int4* ag = reinterpret_cast<const int4*>(aop + (size_t)(b + tid) * aw);
+#pragma unroll
+        for (int c = 0; c < kWidth / 8; c++) *reinterpret_cast<int4*>(as + c * 2048 + off) = ag[c];
+        const int4* bg = reinterpret_cast<const int4*>(bop + (size_t)(b + tid) * bw);
+        for (int c = 0; c < bw / 8; c++) *reinterpret_cast<int4*>(bs + c * 2048 + off) = bg[c];
+        fence_proxy_async_smem();
+        fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            fence_after();
+            const uint32_t aa = smem_u32(as), ba = smem_u32(bs);
+#pragma unroll
+            for (int s = 0; s < 8; s++) mma_f16_ss(tD, make_smem_desc(aa + s * 256, 128, 2048), make_smem_desc(ba + s * 256, 128, 2048), idesc, (it > 0 || s > 0) ? 1u : 0u);
+            mma_commit(&mbar[buf]);
+        }
+    }
+    // drain: the last commit covers every earlier MMA
+    {
+        const int last = (it - 1) & 1;
+        mbar_wait(&mbar[last], phase[last]);
+        fence_after();
+    }
+    // M = 64 accumulators: row 16*warp + lane (lane < 16) of D lives in TMEM lane 32*warp + lane
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int row = warp * 16 + lane;
+    float* out = a.partials + (size_t)blockIdx.x * a.n_mlp;
+    size_t moff = m == 0 ? 0 : (size_t)IN_W * kWidth + (size_t)(m - 1) * kWidth * kWidth;
+    for (int c = 0; c < bw; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(tD + lane_base + c, v);
+        wait_ld();
+        if (lane < 16) {
+            if (m < H) {
+                float4* dst = reinterpret_cast<float4*>(out + moff + (size_t)row * bw + c);
+#pragma unroll
+                for (int q = 0; q < 4; q++) dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+            } else {
+                // output layer computed transposed: D[i][o] -> W_out[o][i]
+#pragma unroll
+                for (int q = 0; q < 16; q++) out[moff + (size_t)(c + q) * kWidth + row] = __uint_as_float(v[q]);
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base_s, 128);
+}
+
+__global__ void __launch_bounds__(256) nrc_reduce_partials_kernel(const float* __restrict__ partials, uint32_t n_chunks, uint32_t n_mlp, float* __restrict__ out) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_mlp) return;
+    float g = 0;
+    for (uint32_t c = 0; c < n_chunks; c++) g += partials[(size_t)c * n_mlp + i];
+    out[i] = g;
+}
+
+// materialise the fp16 MLP gradient (what tcnn keeps in Trainer::param_gradients) without running the optimizer
+__global__ void __launch_bounds__(256) nrc_partials_to_half_kernel(const float* __restrict__ partials, uint32_t n_chunks, uint32_t n_mlp, __half* __restrict__ out) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_mlp) return;
+    float g = 0;
+    for (uint32_t c = 0; c < n_chunks; c++) g += partials[(size_t)c * n_mlp + i];
+    out[i] = __float2half_rn(g);
+}
+
+// ---------------------------------------------------------------------------------------------- optimizer
+struct OptArgs {
+    uint64_t n_params, n_mlp;
+    float* master;
+    __half* w16;
+    __half* ema16;
+    __half* grad16;
+    float* m1;
+    float* m2;
+    uint32_t* steps;
+    const float* partials;
+    uint32_t n_chunks;
+    float lr, beta1, beta2, eps, l2_reg, loss_scale, ema_decay, ema_debias_old, ema_debias_new;
+};
+
+// adam.h:48-121 followed by ema.h:63-76 in one pass over the parameter vector.
+__global__ void __launch_bounds__(256) nrc_optimizer_kernel(const __grid_constant__ OptArgs a) {
+    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= a.n_params) return;
+    __half g16;
+    const bool is_mlp = i < a.n_mlp;
+    if (is_mlp) {
+        float g = 0;
+        for (uint32_t c = 0; c < a.n_chunks; c++) g += a.partials[(size_t)c * a.n_mlp + i];
+        g16 = __float2half_rn(g);          // tcnn keeps gradients in fp16 (trainer.h:322-336)
+        a.grad16[i] = g16;
+    } else {
+        g16 = a.grad16[i];
+    }
+    float gradient = __half2float(g16) / a.loss_scale;
+    __half w = a.w16[i];
+    if (is_mlp || gradient != 0.0f) {
+        const float wfp = a.master[i];
+        if (is_mlp) gradient += a.l2_reg * wfp;
+        const float gsq = gradient * gradient;
+        const float fm = a.m1[i] = a.beta1 * a.m1[i] + (1 - a.beta1) * gradient;
+        const float sm = a.m2[i] = a.beta2 * a.m2[i] + (1 - a.beta2) * gsq;
+        const uint32_t st = ++a.steps[i];
+        const float lr = a.lr * (sqrtf(1 - powf(a.beta2, (float)st)) / (1 - powf(a.beta1, (float)st)));
+        const float eff = fminf(fmaxf(lr / (sqrtf(sm) + a.eps), 0.0f), 3.402823466e+38f);
+        const float nw = wfp - eff * fm;
+        a.master[i] = nw;
+        w = __float2half_rn(nw);
+        a.w16[i] = w;
+        if (!is_mlp) a.grad16[i] = __float2half_rn(0.0f);    // consumed: keeps the encoding gradient zeroed for the next step
+    }
+    const float filtered = (__half2float(a.ema16[i]) * a.ema_decay * a.ema_debias_old + __half2float(w) * (1 - a.ema_decay)) * a.ema_debias_new;
+    a.ema16[i] = __float2half_rn(filtered);
+}
+
+}  // namespace nrchpm

@@ -25,6 +25,7 @@ CONFIGS = [  # name, pos, dir, depth, n_infer, batch, steps
     ("tri_ob_d5", 2, 0, 5, 1024, 256, 16),
     ("hash_tri_d3", 0, 2, 3, 512, 256, 4),
     ("id_id_d2", 1, 1, 2, 512, 256, 4),
+    ("freq_ob_d4", 3, 0, 4, 512, 256, 4),
 ]
 
 
@@ -41,7 +42,10 @@ def make_records(rng, n):
 def main():
     out_root = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out_root, exist_ok=True)
+    only = set(sys.argv[1:])
     for name, pos, dr, depth, n_infer, batch, steps in CONFIGS:
+        if only and name not in only:
+            continue
         rng = np.random.default_rng(1337 + pos * 10 + dr)
         work = os.path.join(out_root, "tcnn_dump_" + name)
         os.makedirs(work, exist_ok=True)

