@@ -144,27 +144,34 @@ static int run_bench() {
 	const int frames = (int)argl("frames", 100), warmup = (int)argl("warmup", 20);
 	const bool train = argl("train", 1) != 0, infer = argl("infer", 1) != 0;
 	TrainableModel model = create_from_config(5, 3, model_config());
-	GPUMemory<float> infer_in((size_t)n_infer * 5), infer_out((size_t)n_infer * 3), train_in((size_t)n_batches * B * 5), train_tgt((size_t)n_batches * B * 3);
+	// `sets` independent record sets are rotated frame by frame so that inputs + outputs exceed the 126 MB L2 (bench.py does the same)
+	const uint32_t n_sets = (uint32_t)argl("sets", 1);
+	std::vector<GPUMemory<float>> infer_in(n_sets), infer_out(n_sets), train_in(n_sets), train_tgt(n_sets);
 	{
 		// synthetic records like bench.py: pos ~ U[0,1)^3 + skySize/2 (Q4), theta ~ U[-.5,1.5), phi ~ U[0,1)
-		std::vector<float> h((size_t)n_infer * 5); pcg32 rng{1337};
+		pcg32 rng{1337};
 		const float off[3] = {31.1585f, 21.1475f, 38.3535f};
-		for (size_t i = 0; i < (size_t)n_infer; i++) { for (int d = 0; d < 3; d++) h[i * 5 + d] = rng.next_float() + off[d]; h[i * 5 + 3] = rng.next_float() * 2 - 0.5f; h[i * 5 + 4] = rng.next_float(); }
-		infer_in.copy_from_host(h);
-		std::vector<float> t((size_t)n_batches * B * 5), g((size_t)n_batches * B * 3);
-		for (size_t i = 0; i < (size_t)n_batches * B; i++) { for (int d = 0; d < 3; d++) t[i * 5 + d] = rng.next_float() + off[d]; t[i * 5 + 3] = rng.next_float() * 2 - 0.5f; t[i * 5 + 4] = rng.next_float(); for (int d = 0; d < 3; d++) g[i * 3 + d] = rng.next_float() * 2; }
-		train_in.copy_from_host(t); train_tgt.copy_from_host(g);
+		for (uint32_t k = 0; k < n_sets; k++) {
+			std::vector<float> h((size_t)n_infer * 5);
+			for (size_t i = 0; i < (size_t)n_infer; i++) { for (int d = 0; d < 3; d++) h[i * 5 + d] = rng.next_float() + off[d]; h[i * 5 + 3] = rng.next_float() * 2 - 0.5f; h[i * 5 + 4] = rng.next_float(); }
+			infer_in[k].resize(h.size()); infer_in[k].copy_from_host(h); infer_out[k].resize((size_t)n_infer * 3);
+			std::vector<float> t((size_t)n_batches * B * 5), g((size_t)n_batches * B * 3);
+			for (size_t i = 0; i < (size_t)n_batches * B; i++) { for (int d = 0; d < 3; d++) t[i * 5 + d] = rng.next_float() + off[d]; t[i * 5 + 3] = rng.next_float() * 2 - 0.5f; t[i * 5 + 4] = rng.next_float(); for (int d = 0; d < 3; d++) g[i * 3 + d] = rng.next_float() * 2; }
+			train_in[k].resize(t.size()); train_in[k].copy_from_host(t); train_tgt[k].resize(g.size()); train_tgt[k].copy_from_host(g);
+		}
 	}
 	cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
 	float loss = 0;
+	uint32_t frame_no = 0;
 	auto frame = [&]() {
+		const uint32_t k = frame_no++ % n_sets;
 		if (infer) for (uint32_t o = 0; o < n_infer; o += infer_batch) {
 			uint32_t n = std::min(infer_batch, n_infer - o);
-			GPUMatrix<float> bi(infer_in.data() + (size_t)o * 5, 5, n), bo(infer_out.data() + (size_t)o * 3, 3, n);
+			GPUMatrix<float> bi(infer_in[k].data() + (size_t)o * 5, 5, n), bo(infer_out[k].data() + (size_t)o * 3, 3, n);
 			model.network->inference(bi, bo);
 		}
 		if (train) for (uint32_t s = 0; s < n_batches; s++) {
-			GPUMatrix<float> bi(train_in.data() + (size_t)s * B * 5, 5, B), bt(train_tgt.data() + (size_t)s * B * 3, 3, B);
+			GPUMatrix<float> bi(train_in[k].data() + (size_t)s * B * 5, 5, B), bt(train_tgt[k].data() + (size_t)s * B * 3, 3, B);
 			auto ctx = model.trainer->training_step(bi, bt);
 			loss = model.trainer->loss(*ctx);
 		}
