@@ -54,6 +54,7 @@ Renderer::Renderer(Scene* scene, NrcCache* nrc, const hpm_render_config& cfg, cu
     if (n_train_) {
         train_in_.allocate((size_t)n_train_ * 5); train_target_.allocate((size_t)n_train_ * 3);
         train_ray_.allocate((size_t)n_train_ * 6); train_flags_.allocate(n_train_);
+        block_totals_.allocate(2 * (size_t)((n_train_ + 255) / 256));
         train_in_.zero(); train_target_.zero();
         // CreateNrcTrainRingBuffer (:841-881): head = tail = 0, every ray pos (0,0,0) dir (0,0,1)
         std::vector<uint32_t> ring(2 + 6 * (size_t)n_train_, 0u);
@@ -109,17 +110,22 @@ void Renderer::pass_gen_rays(const float fr[4]) {
 void Renderer::pass_prep_train(const float fr[4]) {
     if (!n_train_) return;
     NRCHPM_CUDA(cudaMemsetAsync(counters_.ptr + 1, 0, sizeof(unsigned long long), stream_));
+    const uint32_t n_blocks = (n_train_ + 255) / 256;
     {
         TrainSelectArgs a{};
         a.cfg = dcfg_; a.info = info_.ptr; a.origin = origin_.ptr; a.dir = dir_.ptr;
         a.ring = ring_.ptr; a.train_ray = train_ray_.ptr; a.train_flags = train_flags_.ptr;
-        hpm_train_select_kernel<<<1, 1024, 0, stream_>>>(a);
-        check_launch("hpm_train_select_kernel");
+        a.block_totals = block_totals_.ptr; a.n_blocks = n_blocks;
+        hpm_train_count_kernel<<<n_blocks, 256, 0, stream_>>>(a);
+        check_launch("hpm_train_count_kernel");
+        hpm_train_assign_kernel<<<n_blocks, 256, 0, stream_>>>(a);
+        check_launch("hpm_train_assign_kernel");
     }
     {
         TrainTraceArgs a{};
         a.sc = scene_->dev(); a.cfg = dcfg_; a.frame_random = make_float4(fr[0], fr[1], fr[2], fr[3]);
         a.train_ray = train_ray_.ptr; a.train_flags = train_flags_.ptr; a.ring = ring_.ptr;
+        a.block_totals = block_totals_.ptr; a.n_blocks = n_blocks;
         a.train_in = train_in_.ptr; a.train_target = train_target_.ptr; a.lookups = counters_.ptr + 1;
         hpm_train_trace_kernel<<<(n_train_ + 127) / 128, 128, 0, stream_>>>(a);
         check_launch("hpm_train_trace_kernel");

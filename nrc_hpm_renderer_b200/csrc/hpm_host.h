@@ -50,7 +50,7 @@ private:
     uint32_t n_pixels_ = 0, n_train_ = 0, n_filter_ = 0;
     DeviceBuffer<float4> output_, primary_color_;
     DeviceBuffer<float> info_, origin_, dir_, infer_in_, infer_out_, train_in_, train_target_, train_ray_;
-    DeviceBuffer<uint32_t> ring_, filter_, active_list_, active_count_, train_flags_;
+    DeviceBuffer<uint32_t> ring_, filter_, active_list_, active_count_, train_flags_, block_totals_;
     DeviceBuffer<unsigned long long> counters_;
     uint32_t* filter_host_ = nullptr;     // pinned
     cudaEvent_t ev_[7]{};

@@ -68,6 +68,7 @@ private:
     void init_params(uint64_t seed);
     void setup_kernels();
     void ensure_train_scratch(uint32_t B);
+    void launch_shape(uint32_t tiles, uint32_t& grid, uint32_t& threads) const;
 
     NrcConfig cfg_;
     EncParams enc_;

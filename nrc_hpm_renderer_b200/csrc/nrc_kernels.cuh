@@ -74,9 +74,12 @@ __device__ __forceinline__ void encode_record(const EncParams& e, const __half2*
             GridLevel c;
             grid_level_cell(e, l, x0, x1, x2, c);
             const __half2* base = grid + e.level_offset[l];
+            // a corner whose trilinear weight is exactly 0 contributes fma(0, v, r) == r: skip its gather.  With the
+            // reference's position normalisation (coordinates ~30) the fractional part is 0 in every
+            // dimension at the finest level and often at the next ones, so ~13 % of all gathers disappear, bit-exactly.
             __half2 v[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) v[k] = base[c.idx[k]];
+            for (int k = 0; k < 8; k++) v[k] = c.w[k] != 0.0f ? base[c.idx[k]] : __float2half2_rn(0.0f);
             __half2 r = __float2half2_rn(0.0f);
 #pragma unroll
             for (int k = 0; k < 8; k++) r = __hfma2(__half2half2(__float2half_rn(c.w[k])), v[k], r);   // grid.h:144-163: fp16 fma
@@ -232,6 +235,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) nrc_forward_kernel(const __gri
     __shared__ uint32_t tmem_base_s;
     __shared__ float loss_red[2][4];
     const int tid = threadIdx.x, wg = tid >> 7, r = tid & 127, warp = tid >> 5, lane = tid & 31;
+    const int nthreads = blockDim.x, nwg = nthreads >> 7;      // 2 warpgroups per CTA for large batches, 1 for small ones
     const int H = a.n_hidden;
     uint8_t* w0_s = smem;
     uint8_t* wh_s = w0_s + IN_W * 128;
@@ -240,9 +244,9 @@ __global__ void __launch_bounds__(kFwdThreads, 2) nrc_forward_kernel(const __gri
 
     if (warp == 0) { tmem_alloc(&tmem_base_s, 2 * kColsPerWg); tmem_relinquish(); }
     if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); fence_mbar_init(); }
-    copy_weights_kmajor(w0_s, a.params, kWidth, IN_W, tid, kFwdThreads);
-    for (int l = 1; l < H; l++) copy_weights_kmajor(wh_s + (l - 1) * 8192, a.params + IN_W * kWidth + (l - 1) * kWidth * kWidth, kWidth, kWidth, tid, kFwdThreads);
-    copy_weights_kmajor(wo_s, a.params + IN_W * kWidth + (H - 1) * kWidth * kWidth, kOutPad, kWidth, tid, kFwdThreads);
+    copy_weights_kmajor(w0_s, a.params, kWidth, IN_W, tid, nthreads);
+    for (int l = 1; l < H; l++) copy_weights_kmajor(wh_s + (l - 1) * 8192, a.params + IN_W * kWidth + (l - 1) * kWidth * kWidth, kWidth, kWidth, tid, nthreads);
+    copy_weights_kmajor(wo_s, a.params + IN_W * kWidth + (H - 1) * kWidth * kWidth, kOutPad, kWidth, tid, nthreads);
     fence_proxy_async_smem();
     fence_before();
     __syncthreads();
@@ -260,7 +264,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) nrc_forward_kernel(const __gri
     if (a.d_count) n = min(n, *a.d_count);
     const uint32_t n_tiles = (n + kTile - 1) / kTile;
 
-    for (uint32_t tile = blockIdx.x * 2 + wg; tile < n_tiles; tile += gridDim.x * 2) {
+    for (uint32_t tile = blockIdx.x * nwg + wg; tile < n_tiles; tile += gridDim.x * nwg) {
         const uint32_t row = tile * kTile + r;
         const bool valid = row < n;
         uint32_t rec = 0;
@@ -420,6 +424,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) nrc_backward_kernel(const __gr
     __shared__ uint64_t mbar[2];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, wg = tid >> 7, r = tid & 127, warp = tid >> 5;
+    const int nthreads = blockDim.x, nwg = nthreads >> 7;
     const int H = a.n_hidden;
     uint8_t* w0_s = smem;
     uint8_t* wh_s = w0_s + IN_W * 128;
@@ -432,9 +437,9 @@ __global__ void __launch_bounds__(kFwdThreads, 2) nrc_backward_kernel(const __gr
         for (uint32_t i = 0; i < a.n_loss_partials; i++) s += a.loss_partials[i];
         *a.loss_out = s;
     }
-    copy_weights_mnmajor(w0_s, a.params, kWidth, IN_W, tid, kFwdThreads);
-    for (int l = 1; l < H; l++) copy_weights_mnmajor(wh_s + (l - 1) * 8192, a.params + IN_W * kWidth + (l - 1) * kWidth * kWidth, kWidth, kWidth, tid, kFwdThreads);
-    copy_weights_mnmajor(wo_s, a.params + IN_W * kWidth + (H - 1) * kWidth * kWidth, kOutPad, kWidth, tid, kFwdThreads);
+    copy_weights_mnmajor(w0_s, a.params, kWidth, IN_W, tid, nthreads);
+    for (int l = 1; l < H; l++) copy_weights_mnmajor(wh_s + (l - 1) * 8192, a.params + IN_W * kWidth + (l - 1) * kWidth * kWidth, kWidth, kWidth, tid, nthreads);
+    copy_weights_mnmajor(wo_s, a.params + IN_W * kWidth + (H - 1) * kWidth * kWidth, kOutPad, kWidth, tid, nthreads);
     fence_proxy_async_smem();
     fence_before();
     __syncthreads();
@@ -448,7 +453,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) nrc_backward_kernel(const __gr
     uint32_t phase = 0;
     const uint32_t n_tiles = a.n / kTile;
 
-    for (uint32_t tile = blockIdx.x * 2 + wg; tile < n_tiles; tile += gridDim.x * 2) {
+    for (uint32_t tile = blockIdx.x * nwg + wg; tile < n_tiles; tile += gridDim.x * nwg) {
         const uint32_t row = tile * kTile + r;
         {   // dL/doutput row -> A operand (K = 16)
             const int4* src = reinterpret_cast<const int4*>(a.dout16 + (size_t)row * kOutPad);
@@ -673,42 +678,90 @@ struct OptArgs {
     uint32_t* steps;
     const float* partials;
     uint32_t n_chunks;
-    float lr, beta1, beta2, eps, l2_reg, loss_scale, ema_decay, ema_debias_old, ema_debias_new;
+    float lr, beta1, beta2, eps, l2_reg, loss_scale, ema_decay, ema_debias_old, ema_debias_new, log2_beta1, log2_beta2;
 };
 
-// adam.h:48-121 followed by ema.h:63-76 in one pass over the parameter vector.
+// adam.h:48-121 followed by ema.h:63-76 in one pass over the parameter vector.  Eight consecutive parameters per thread
+// (128-bit accesses to the fp16 vectors).  Encoding entries whose gradient is zero skip Adam (adam.h:77-80); the touched ones
+// are few and scattered, so each warp first compacts them (ballot + popc ranks into a shared list) and then runs Adam
+// densely, 32 touched parameters per iteration, instead of executing eight mostly-predicated-off copies of the update.
+__device__ __forceinline__ __half adam_one(const OptArgs& a, uint64_t i, bool is_mlp, float gradient) {
+    const float wfp = a.master[i];
+    if (is_mlp) gradient += a.l2_reg * wfp;
+    const float gsq = gradient * gradient;
+    const float fm = a.m1[i] = a.beta1 * a.m1[i] + (1 - a.beta1) * gradient;
+    const float sm = a.m2[i] = a.beta2 * a.m2[i] + (1 - a.beta2) * gsq;
+    const uint32_t st = ++a.steps[i];
+    // beta^t as exp2(t * log2 beta): MUFU.EX2 instead of powf's ~100-instruction slow path (relative error ~1e-7)
+    const float lr = a.lr * (sqrtf(1 - exp2f((float)st * a.log2_beta2)) / (1 - exp2f((float)st * a.log2_beta1)));
+    const float eff = fminf(fmaxf(lr / (sqrtf(sm) + a.eps), 0.0f), 3.402823466e+38f);
+    const float nw = wfp - eff * fm;
+    a.master[i] = nw;
+    return __float2half_rn(nw);
+}
+
 __global__ void __launch_bounds__(256) nrc_optimizer_kernel(const __grid_constant__ OptArgs a) {
-    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= a.n_params) return;
-    __half g16;
-    const bool is_mlp = i < a.n_mlp;
+    __shared__ uint16_t s_el[8][256];
+    __shared__ __half s_g[8][256];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t i0 = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 8;
+    const uint64_t warp_i0 = ((uint64_t)blockIdx.x * 256 + warp * 32) * 8;
+    if (warp_i0 >= a.n_params) return;                       // whole warp out of range
+    const bool in_range = i0 < a.n_params;
+    const bool is_mlp = warp_i0 < a.n_mlp;                   // n_mlp is a multiple of 256: a warp never straddles the boundary
+    union V8 { int4 v; __half h[8]; uint32_t u[4]; };
+    V8 g, w, e;
+    g.v = make_int4(0, 0, 0, 0);
+    const float inv_scale = 1.0f / a.loss_scale;
     if (is_mlp) {
-        float g = 0;
-        for (uint32_t c = 0; c < a.n_chunks; c++) g += a.partials[(size_t)c * a.n_mlp + i];
-        g16 = __float2half_rn(g);          // tcnn keeps gradients in fp16 (trainer.h:322-336)
-        a.grad16[i] = g16;
+        // network weights: every parameter is updated; gradient = fixed-order sum of the weight-gradient partials
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (uint32_t c = 0; c < a.n_chunks; c++) {
+            const float4* p = reinterpret_cast<const float4*>(a.partials + (size_t)c * a.n_mlp + i0);
+            const float4 p0 = p[0], p1 = p[1];
+            acc[0] += p0.x; acc[1] += p0.y; acc[2] += p0.z; acc[3] += p0.w; acc[4] += p1.x; acc[5] += p1.y; acc[6] += p1.z; acc[7] += p1.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) g.h[j] = __float2half_rn(acc[j]);      // tcnn keeps gradients in fp16 (trainer.h:322-336)
+        *reinterpret_cast<int4*>(a.grad16 + i0) = g.v;
+#pragma unroll
+        for (int j = 0; j < 8; j++) w.h[j] = adam_one(a, i0 + j, true, __half2float(g.h[j]) * inv_scale);
+        *reinterpret_cast<int4*>(a.w16 + i0) = w.v;
     } else {
-        g16 = a.grad16[i];
+        if (in_range) g.v = *reinterpret_cast<const int4*>(a.grad16 + i0);
+        uint32_t base = 0, my_rank[8];
+        bool mine[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            mine[j] = __half2float(g.h[j]) != 0.0f;
+            const uint32_t b = __ballot_sync(0xffffffffu, mine[j]);
+            my_rank[j] = base + __popc(b & ((1u << lane) - 1));
+            base += __popc(b);
+        }
+        if (base) {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (mine[j]) { s_el[warp][my_rank[j]] = (uint16_t)(lane * 8 + j); s_g[warp][my_rank[j]] = g.h[j]; }
+            __syncwarp();
+            for (uint32_t r = lane; r < base; r += 32) {
+                const uint64_t i = warp_i0 + s_el[warp][r];
+                a.w16[i] = adam_one(a, i, false, __half2float(s_g[warp][r]) * inv_scale);
+            }
+            __syncwarp();
+            if (in_range && ((g.u[0] | g.u[1] | g.u[2] | g.u[3]) & 0x7fff7fffu)) *reinterpret_cast<int4*>(a.grad16 + i0) = make_int4(0, 0, 0, 0);   // consumed
+        }
+        if (in_range) w.v = *reinterpret_cast<const int4*>(a.w16 + i0);
     }
-    float gradient = __half2float(g16) / a.loss_scale;
-    __half w = a.w16[i];
-    if (is_mlp || gradient != 0.0f) {
-        const float wfp = a.master[i];
-        if (is_mlp) gradient += a.l2_reg * wfp;
-        const float gsq = gradient * gradient;
-        const float fm = a.m1[i] = a.beta1 * a.m1[i] + (1 - a.beta1) * gradient;
-        const float sm = a.m2[i] = a.beta2 * a.m2[i] + (1 - a.beta2) * gsq;
-        const uint32_t st = ++a.steps[i];
-        const float lr = a.lr * (sqrtf(1 - powf(a.beta2, (float)st)) / (1 - powf(a.beta1, (float)st)));
-        const float eff = fminf(fmaxf(lr / (sqrtf(sm) + a.eps), 0.0f), 3.402823466e+38f);
-        const float nw = wfp - eff * fm;
-        a.master[i] = nw;
-        w = __float2half_rn(nw);
-        a.w16[i] = w;
-        if (!is_mlp) a.grad16[i] = __float2half_rn(0.0f);    // consumed: keeps the encoding gradient zeroed for the next step
+    if (!in_range) return;
+    e.v = *reinterpret_cast<const int4*>(a.ema16 + i0);
+    const float k_old = a.ema_decay * a.ema_debias_old, k_new = 1 - a.ema_decay;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const float filtered = (__half2float(e.h[j]) * a.ema_decay * a.ema_debias_old + __half2float(w.h[j]) * (1 - a.ema_decay)) * a.ema_debias_new;
+        e.h[j] = __float2half_rn(filtered);
     }
-    const float filtered = (__half2float(a.ema16[i]) * a.ema_decay * a.ema_debias_old + __half2float(w) * (1 - a.ema_decay)) * a.ema_debias_new;
-    a.ema16[i] = __float2half_rn(filtered);
+    (void)k_old; (void)k_new;
+    *reinterpret_cast<int4*>(a.ema16 + i0) = e.v;
 }
 
 }  // namespace nrchpm
