@@ -74,12 +74,30 @@ __device__ __forceinline__ void encode_record(const EncParams& e, const __half2*
             GridLevel c;
             grid_level_cell(e, l, x0, x1, x2, c);
             const __half2* base = grid + e.level_offset[l];
-            // a corner whose trilinear weight is exactly 0 contributes fma(0, v, r) == r: skip its gather.  With the
-            // reference's position normalisation (coordinates ~30) the fractional part is 0 in every
-            // dimension at the finest level and often at the next ones, so ~13 % of all gathers disappear, bit-exactly.
+            // Gather diet (bit-exact):
+            //  * a corner whose trilinear weight is exactly 0 contributes fma(0, v, r) == r, so its load is skipped.  With the
+            //    reference's position normalisation (coordinates ~30) the fractional part is 0 in every
+            //    dimension at the finest level and often at the next ones: ~13 % of all gathers disappear;
+            //  * the two corners of an x-edge sit in ONE aligned 8-byte word whenever their indices differ only in bit 0
+            //    (dense levels: x even; coherent-prime hash, whose x prime is 1: x even) -> one 64-bit load instead of
+            //    two 32-bit loads, i.e. one L1 wavefront instead of two for half of all edges.
             __half2 v[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) v[k] = c.w[k] != 0.0f ? base[c.idx[k]] : __float2half2_rn(0.0f);
+            for (int k = 0; k < 8; k += 2) {
+                const uint32_t i0 = c.idx[k], i1 = c.idx[k + 1];
+                const bool n0 = c.w[k] != 0.0f, n1 = c.w[k + 1] != 0.0f;
+                const bool paired = (i0 ^ i1) == 1u;
+                // predicated, branch-free: one 64-bit load of the aligned word holding corner 0 (and corner 1 when paired),
+                // plus a 32-bit load of corner 1 only when it lives elsewhere
+                uint2 q = make_uint2(0u, 0u);
+                if (n0 | (paired & n1)) q = *reinterpret_cast<const uint2*>(base + (i0 & ~1u));
+                uint32_t a1 = 0u;
+                if (!paired & n1) a1 = *reinterpret_cast<const uint32_t*>(base + i1);
+                const uint32_t a0 = (i0 & 1u) ? q.y : q.x;
+                a1 = paired ? ((i1 & 1u) ? q.y : q.x) : a1;
+                v[k] = *reinterpret_cast<const __half2*>(&a0);
+                v[k + 1] = *reinterpret_cast<const __half2*>(&a1);
+            }
             __half2 r = __float2half2_rn(0.0f);
 #pragma unroll
             for (int k = 0; k < 8; k++) r = __hfma2(__half2half2(__float2half_rn(c.w[k])), v[k], r);   // grid.h:144-163: fp16 fma
