@@ -156,7 +156,9 @@ struct Ctx {
                 float sqr_term = (1.0f - g * g) / (1.0f - g + (2.0f * g * rand_float(1.0f)));
                 cos_theta = (1.0f + (g * g) - (sqr_term * sqr_term)) / (2.0f * g);
             }
-            angle = std::acos(cos_theta);
+            // GLSL leaves acos undefined outside [-1, 1]; fp32 rounding yields cos_theta = -1.0000004 for u == 0.  The bundled
+            // reference/*/0.exr (8192 blended frames) contain no NaN, so the reference's driver returns a finite angle: clamp.
+            angle = std::acos(std::fmin(1.0f, std::fmax(-1.0f, cos_theta)));
         } else {
             angle = rand_float(PI_F);
         }
