@@ -147,7 +147,7 @@ def cpu_baseline_leg():
     O.build()
     o = O.NrcOracle(O.nrc_config(0, 0, 6))
     rng = np.random.default_rng(1337)
-    n_i, n_t = 1 << 16, 1 << 12
+    n_i, n_t = N_INFER, TRAIN_BATCH            # one full frame of inference records + one 2^14 training step (~10-20 s of host time)
     rec, tin, tgt = synth_records(rng, n_i), synth_records(rng, n_t), (rng.random((n_t, 3), dtype=np.float32) * 2).astype(np.float32)
     t0 = time.perf_counter()
     o.inference(rec)
@@ -155,7 +155,7 @@ def cpu_baseline_leg():
     t = time.perf_counter() - t0
     cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
     return {"value": (n_i + n_t) / t, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"oracle/nrc_oracle.cpp (OpenMP): {n_i} inference + one {n_t}-record training step, {t:.1f} s"}
+            "sample": f"oracle/nrc_oracle.cpp (OpenMP, {cores} threads): {n_i} inference records + one {n_t}-record training step, {t:.1f} s"}
 
 
 def frame_leg(torch, stream, steps, warmup):
@@ -291,7 +291,7 @@ def run_ours(args):
         e2e_step(i)
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = max(3, min(args.steps, 50))
     for i in range(e2e_steps):
         e2e_step(i)
     torch.cuda.synchronize()
@@ -325,7 +325,7 @@ def run_ours(args):
                 out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
             if not args.no_frame:
                 try:
-                    out["frame"] = frame_leg(torch, sp, steps=max(3, min(args.steps, 10)), warmup=3)
+                    out["frame"] = frame_leg(torch, sp, steps=max(3, min(args.steps, 30)), warmup=5)
                 except Exception as e:
                     out["frame"] = {"error": str(e)[:300]}
         print(json.dumps(out))
@@ -337,8 +337,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-frame", action="store_true", help="skip the full-frame leg (tracking + NRC + compositing)")
     args = ap.parse_args()

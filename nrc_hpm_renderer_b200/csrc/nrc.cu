@@ -208,7 +208,10 @@ NrcCache::NrcCache(const NrcConfig& cfg, uint64_t seed) : cfg_(cfg) {
     setup_kernels();
 }
 
-NrcCache::~NrcCache() {}
+NrcCache::~NrcCache() {
+    for (auto e : pipe_events_) cudaEventDestroy(e);
+    if (copy_in_stream_) { cudaStreamDestroy(copy_in_stream_); cudaStreamDestroy(copy_out_stream_); cudaStreamDestroy(compute_stream_); }
+}
 
 void NrcCache::set_params_fp32(const float* host_master) {
     NRCHPM_CUDA(cudaMemcpy(master_.ptr, host_master, n_params_ * sizeof(float), cudaMemcpyHostToDevice));
@@ -527,13 +530,38 @@ void NrcCache::gradient_buffers(float** mlp, void** enc) {
     if (mlp) *mlp = mlp_grad_f32_.ptr;
     if (enc) *enc = n_grid_ ? (void*)(grad16_.ptr + n_mlp_) : nullptr;
 }
+// Host-buffer inference: the records are cut into chunks of whole persistent-grid rounds and pipelined over three streams
+// (H2D copy, compute, D2H copy), so PCIe transfers of chunk i+1 / i-1 overlap the kernel of chunk i.
 void NrcCache::inference_host(const float* h_in, float* h_out, uint32_t n, bool use_ema) {
+    if (n == 0) return;
     host_in_.ensure((size_t)n * 5); host_out_.ensure((size_t)n * 3);
-    cudaStream_t s = stream_;
-    NRCHPM_CUDA(cudaMemcpyAsync(host_in_.ptr, h_in, (size_t)n * 5 * sizeof(float), cudaMemcpyHostToDevice, s));
-    inference(host_in_.ptr, host_out_.ptr, n, use_ema, nullptr, nullptr, s);
-    NRCHPM_CUDA(cudaMemcpyAsync(h_out, host_out_.ptr, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
-    NRCHPM_CUDA(cudaStreamSynchronize(s));
+    if (!copy_in_stream_) {
+        NRCHPM_CUDA(cudaStreamCreateWithFlags(&copy_in_stream_, cudaStreamNonBlocking));
+        NRCHPM_CUDA(cudaStreamCreateWithFlags(&copy_out_stream_, cudaStreamNonBlocking));
+        NRCHPM_CUDA(cudaStreamCreateWithFlags(&compute_stream_, cudaStreamNonBlocking));
+    }
+    const uint32_t chunk = (uint32_t)sm_count_ * 2 * 2 * 4 * kTile;       // 4 tiles per resident warpgroup
+    const uint32_t n_chunks = (n + chunk - 1) / chunk;
+    while (pipe_events_.size() < 2 * (size_t)n_chunks + 1) {
+        cudaEvent_t e; NRCHPM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        pipe_events_.push_back(e);
+    }
+    // everything already queued on the cache's stream (e.g. a training step that changed the weights) comes first
+    cudaEvent_t ev_prev = pipe_events_[2 * (size_t)n_chunks];
+    NRCHPM_CUDA(cudaEventRecord(ev_prev, stream_));
+    NRCHPM_CUDA(cudaStreamWaitEvent(compute_stream_, ev_prev, 0));
+    NRCHPM_CUDA(cudaStreamWaitEvent(copy_in_stream_, ev_prev, 0));
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        const uint32_t o = c * chunk, m = std::min(chunk, n - o);
+        NRCHPM_CUDA(cudaMemcpyAsync(host_in_.ptr + (size_t)o * 5, h_in + (size_t)o * 5, (size_t)m * 5 * sizeof(float), cudaMemcpyHostToDevice, copy_in_stream_));
+        NRCHPM_CUDA(cudaEventRecord(pipe_events_[2 * c], copy_in_stream_));
+        NRCHPM_CUDA(cudaStreamWaitEvent(compute_stream_, pipe_events_[2 * c], 0));
+        inference(host_in_.ptr + (size_t)o * 5, host_out_.ptr + (size_t)o * 3, m, use_ema, nullptr, nullptr, compute_stream_);
+        NRCHPM_CUDA(cudaEventRecord(pipe_events_[2 * c + 1], compute_stream_));
+        NRCHPM_CUDA(cudaStreamWaitEvent(copy_out_stream_, pipe_events_[2 * c + 1], 0));
+        NRCHPM_CUDA(cudaMemcpyAsync(h_out + (size_t)o * 3, host_out_.ptr + (size_t)o * 3, (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToHost, copy_out_stream_));
+    }
+    NRCHPM_CUDA(cudaStreamSynchronize(copy_out_stream_));
 }
 void NrcCache::training_step_host(const float* h_in, const float* h_tgt, uint32_t B, float* loss_out) {
     host_in_.ensure((size_t)B * 5); host_tgt_.ensure((size_t)B * 3);

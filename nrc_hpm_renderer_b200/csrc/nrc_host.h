@@ -88,6 +88,8 @@ private:
     cudaExternalSemaphore_t start_sem_ = nullptr, finished_sem_ = nullptr;
     cudaStream_t stream_ = nullptr;
     std::vector<std::pair<uint32_t, uint32_t>> infer_batches_;   // (first record, count)
+    cudaStream_t copy_in_stream_ = nullptr, copy_out_stream_ = nullptr, compute_stream_ = nullptr;   // host-buffer pipeline
+    std::vector<cudaEvent_t> pipe_events_;
 };
 
 }  // namespace nrchpm

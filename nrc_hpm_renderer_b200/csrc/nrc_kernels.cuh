@@ -48,6 +48,7 @@ __device__ __forceinline__ void grid_level_cell(const EncParams& e, int l, float
     }
     const uint32_t hs = e.level_hsize[l], s0 = e.level_s0[l], s1 = e.level_s1[l], s2 = e.level_s2[l];
     const bool hashed = e.level_hash[l] != 0;
+    const bool pow2 = (hs & (hs - 1)) == 0;        // `% hashmap_size` is a mask for power-of-two tables (every level of the presets)
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         float w = 1;
@@ -57,7 +58,7 @@ __device__ __forceinline__ void grid_level_cell(const EncParams& e, int l, float
             if ((k & (1 << d)) == 0) { w *= 1 - p[d]; q[d] = g[d]; } else { w *= p[d]; q[d] = g[d] + 1; }
         }
         uint32_t index = hashed ? ((q[0] * 1u) ^ (q[1] * 2654435761u) ^ (q[2] * 805459861u)) : (q[0] * s0 + q[1] * s1 + q[2] * s2);
-        c.idx[k] = index % hs;
+        c.idx[k] = pow2 ? (index & (hs - 1)) : (index % hs);
         c.w[k] = w;
     }
 }
