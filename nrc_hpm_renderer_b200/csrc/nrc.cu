@@ -188,6 +188,13 @@ void NrcCache::init_params(uint64_t seed) {
     NRCHPM_CUDA(cudaMemset(m1_.ptr, 0, m1_.bytes()));
     NRCHPM_CUDA(cudaMemset(m2_.ptr, 0, m2_.bytes()));
     NRCHPM_CUDA(cudaMemset(steps_.ptr, 0, steps_.bytes()));
+    if (n_grid_) {      // moments and step counters of the encoding: zero everything but the master weights just written
+        DeviceBuffer<float> zeros;
+        zeros.allocate(n_grid_);
+        zeros.zero();
+        for (int field = 1; field <= 3; field++) scatter_grid_field(field, zeros.ptr);
+        NRCHPM_CUDA(cudaDeviceSynchronize());
+    }
     NRCHPM_CUDA(cudaMemset(grad16_.ptr, 0, grad16_.bytes()));
     current_step_ = 0;
 }
@@ -200,8 +207,9 @@ NrcCache::NrcCache(const NrcConfig& cfg, uint64_t seed) : cfg_(cfg) {
     NRCHPM_CUDA(cudaGetDeviceProperties(&prop, dev));
     if (prop.major != 10) throw Error(NRCHPM_ERR_CUDA, std::string("this library contains sm_100a code only; device is ") + prop.name);
     sm_count_ = prop.multiProcessorCount;
-    master_.allocate(n_params_); w16_.allocate(n_params_); ema16_.allocate(n_params_); grad16_.allocate(n_params_);
-    m1_.allocate(n_params_); m2_.allocate(n_params_); steps_.allocate(n_params_);
+    w16_.allocate(n_params_); ema16_.allocate(n_params_); grad16_.allocate(n_params_);
+    master_.allocate(n_mlp_); m1_.allocate(n_mlp_); m2_.allocate(n_mlp_); steps_.allocate(n_mlp_);      // network weights: SoA
+    grid_state_.allocate(n_grid_ / 2);                                                                    // encoding: one record per entry
     loss_dev_.allocate(1);
     NRCHPM_CUDA(cudaMemset(loss_dev_.ptr, 0, sizeof(float)));
     init_params(seed);
@@ -213,8 +221,22 @@ NrcCache::~NrcCache() {
     if (copy_in_stream_) { cudaStreamDestroy(copy_in_stream_); cudaStreamDestroy(copy_out_stream_); cudaStreamDestroy(compute_stream_); }
 }
 
+void NrcCache::scatter_grid_field(int field, const float* d_src) {
+    const uint64_t n = n_grid_ / 2;
+    nrc_grid_state_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, nullptr>>>(grid_state_.ptr, n, field, d_src);
+    check_launch("nrc_grid_state_scatter_kernel");
+}
+
 void NrcCache::set_params_fp32(const float* host_master) {
-    NRCHPM_CUDA(cudaMemcpy(master_.ptr, host_master, n_params_ * sizeof(float), cudaMemcpyHostToDevice));
+    NRCHPM_CUDA(cudaDeviceSynchronize());
+    NRCHPM_CUDA(cudaMemcpy(master_.ptr, host_master, n_mlp_ * sizeof(float), cudaMemcpyHostToDevice));
+    if (n_grid_) {
+        DeviceBuffer<float> tmp;
+        tmp.allocate(n_grid_);
+        NRCHPM_CUDA(cudaMemcpy(tmp.ptr, host_master + n_mlp_, n_grid_ * sizeof(float), cudaMemcpyHostToDevice));
+        scatter_grid_field(0, tmp.ptr);
+        NRCHPM_CUDA(cudaDeviceSynchronize());
+    }
     std::vector<__half> h(n_params_);
     for (size_t i = 0; i < n_params_; i++) h[i] = __float2half_rn(host_master[i]);
     NRCHPM_CUDA(cudaMemcpy(w16_.ptr, h.data(), n_params_ * sizeof(__half), cudaMemcpyHostToDevice));
@@ -233,18 +255,30 @@ void NrcCache::get_params(int which, float* out) {
         check_launch("nrc_partials_to_half_kernel");
     }
     NRCHPM_CUDA(cudaDeviceSynchronize());
-    if (which == 0 || which == 4 || which == 5) {
-        const float* src = which == 0 ? master_.ptr : which == 4 ? m1_.ptr : m2_.ptr;
-        NRCHPM_CUDA(cudaMemcpy(out, src, n_params_ * sizeof(float), cudaMemcpyDeviceToHost));
+    if (which == 0 || which == 4 || which == 5 || which == 6) {
+        // network part: SoA arrays; encoding part: gathered out of the per-entry records into tcnn's parameter order
+        if (which == 6) {
+            std::vector<uint32_t> h(n_mlp_);
+            NRCHPM_CUDA(cudaMemcpy(h.data(), steps_.ptr, n_mlp_ * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < n_mlp_; i++) out[i] = (float)h[i];
+        } else {
+            const float* src = which == 0 ? master_.ptr : which == 4 ? m1_.ptr : m2_.ptr;
+            NRCHPM_CUDA(cudaMemcpy(out, src, n_mlp_ * sizeof(float), cudaMemcpyDeviceToHost));
+        }
+        if (n_grid_) {
+            DeviceBuffer<float> tmp;
+            tmp.allocate(n_grid_);
+            const uint64_t n = n_grid_ / 2;
+            const int field = which == 0 ? 0 : which == 4 ? 1 : which == 5 ? 2 : 3;
+            nrc_grid_state_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, nullptr>>>(grid_state_.ptr, n, field, tmp.ptr);
+            check_launch("nrc_grid_state_gather_kernel");
+            NRCHPM_CUDA(cudaMemcpy(out + n_mlp_, tmp.ptr, n_grid_ * sizeof(float), cudaMemcpyDeviceToHost));
+        }
     } else if (which >= 1 && which <= 3) {
         std::vector<__half> h(n_params_);
         const __half* src = which == 1 ? w16_.ptr : which == 2 ? ema16_.ptr : grad16_.ptr;
         NRCHPM_CUDA(cudaMemcpy(h.data(), src, n_params_ * sizeof(__half), cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < n_params_; i++) out[i] = __half2float(h[i]);
-    } else if (which == 6) {
-        std::vector<uint32_t> h(n_params_);
-        NRCHPM_CUDA(cudaMemcpy(h.data(), steps_.ptr, n_params_ * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < n_params_; i++) out[i] = (float)h[i];
     } else throw Error(NRCHPM_ERR_INVALID, "nrc_get_params: which must be 0..6");
 }
 
@@ -362,6 +396,7 @@ void NrcCache::optimizer_step(cudaStream_t s) {
     OptArgs a{};
     a.n_params = n_params_; a.n_mlp = n_mlp_;
     a.master = master_.ptr; a.w16 = w16_.ptr; a.ema16 = ema16_.ptr; a.grad16 = grad16_.ptr; a.m1 = m1_.ptr; a.m2 = m2_.ptr; a.steps = steps_.ptr;
+    a.grid_state = grid_state_.ptr;
     a.partials = dw_source_ ? dw_source_ : dw_partials_.ptr; a.n_chunks = dw_source_ ? 1u : dw_chunks_;
     a.lr = cfg_.learning_rate; a.beta1 = cfg_.beta1; a.beta2 = cfg_.beta2; a.eps = cfg_.epsilon; a.l2_reg = cfg_.l2_reg; a.loss_scale = cfg_.loss_scale;
     a.ema_decay = cfg_.ema_decay;

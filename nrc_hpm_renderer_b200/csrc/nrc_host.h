@@ -67,6 +67,7 @@ private:
     void derive();
     void init_params(uint64_t seed);
     void setup_kernels();
+    void scatter_grid_field(int field, const float* d_src);
     void ensure_train_scratch(uint32_t B);
     void launch_shape(uint32_t tiles, uint32_t& grid, uint32_t& threads) const;
 
@@ -77,6 +78,7 @@ private:
     DeviceBuffer<float> master_, m1_, m2_, loss_dev_, loss_partials_, dw_partials_, mlp_grad_f32_;
     DeviceBuffer<__half> w16_, ema16_, grad16_, x16_, acts_, dacts_, out16_, dout16_, dx16_;
     DeviceBuffer<uint32_t> steps_;
+    DeviceBuffer<GridAdamState> grid_state_;       // Adam state of the encoding parameters, one 32-byte record per entry
     DeviceBuffer<float> host_in_, host_out_, host_tgt_;
     uint32_t scratch_batch_ = 0, last_batch_ = 0, dw_chunks_ = 0, current_step_ = 0;
     const float* dw_source_ = nullptr;

@@ -688,40 +688,41 @@ __global__ void __launch_bounds__(256) nrc_partials_to_half_kernel(const float* 
 // ---------------------------------------------------------------------------------------------- optimizer
 struct OptArgs {
     uint64_t n_params, n_mlp;
-    float* master;
-    __half* w16;
-    __half* ema16;
-    __half* grad16;
+    float* master;              // network weights only (SoA, n_mlp)
     float* m1;
     float* m2;
     uint32_t* steps;
+    GridAdamState* grid_state;  // one 32-byte record per hash-grid entry
+    __half* w16;
+    __half* ema16;
+    __half* grad16;
     const float* partials;
     uint32_t n_chunks;
     float lr, beta1, beta2, eps, l2_reg, loss_scale, ema_decay, ema_debias_old, ema_debias_new, log2_beta1, log2_beta2;
 };
 
-// adam.h:48-121 followed by ema.h:63-76 in one pass over the parameter vector.  Eight consecutive parameters per thread
-// (128-bit accesses to the fp16 vectors).  Encoding entries whose gradient is zero skip Adam (adam.h:77-80); the touched ones
-// are few and scattered, so each warp first compacts them (ballot + popc ranks into a shared list) and then runs Adam
-// densely, 32 touched parameters per iteration, instead of executing eight mostly-predicated-off copies of the update.
-__device__ __forceinline__ __half adam_one(const OptArgs& a, uint64_t i, bool is_mlp, float gradient) {
-    const float wfp = a.master[i];
-    if (is_mlp) gradient += a.l2_reg * wfp;
+// adam.h:48-121 for one parameter whose state is already in registers; returns the new fp32 master weight
+__device__ __forceinline__ float adam_update(const OptArgs& a, float wfp, float& m1, float& m2, uint32_t& st, float gradient) {
     const float gsq = gradient * gradient;
-    const float fm = a.m1[i] = a.beta1 * a.m1[i] + (1 - a.beta1) * gradient;
-    const float sm = a.m2[i] = a.beta2 * a.m2[i] + (1 - a.beta2) * gsq;
-    const uint32_t st = ++a.steps[i];
+    m1 = a.beta1 * m1 + (1 - a.beta1) * gradient;
+    m2 = a.beta2 * m2 + (1 - a.beta2) * gsq;
+    st++;
     // beta^t as exp2(t * log2 beta): MUFU.EX2 instead of powf's ~100-instruction slow path (relative error ~1e-7)
     const float lr = a.lr * (sqrtf(1 - exp2f((float)st * a.log2_beta2)) / (1 - exp2f((float)st * a.log2_beta1)));
-    const float eff = fminf(fmaxf(lr / (sqrtf(sm) + a.eps), 0.0f), 3.402823466e+38f);
-    const float nw = wfp - eff * fm;
-    a.master[i] = nw;
-    return __float2half_rn(nw);
+    const float eff = fminf(fmaxf(lr / (sqrtf(m2) + a.eps), 0.0f), 3.402823466e+38f);
+    return wfp - eff * m1;
 }
 
+// adam.h:48-121 followed by ema.h:63-76 in one pass over the parameter vector.  Eight consecutive parameters per thread
+// (128-bit accesses to the fp16 vectors; gradient, weights and EMA are requested up front).  Encoding entries whose gradient
+// is zero skip Adam (adam.h:77-80); the touched ones are few and scattered, so each warp first compacts them (ballot + popc
+// ranks into a shared list) and then runs Adam densely, one touched ENTRY (two features, one 32-byte state sector) per lane,
+// instead of executing mostly-predicated-off copies of the update.  The new fp16 weights travel back to their owner thread
+// through shared memory, so weights, EMA and the re-zeroed gradient are written with full 128-bit stores.
 __global__ void __launch_bounds__(256) nrc_optimizer_kernel(const __grid_constant__ OptArgs a) {
-    __shared__ uint16_t s_el[8][256];
-    __shared__ __half s_g[8][256];
+    __shared__ uint32_t s_g[8][128];       // per warp: compacted gradients (half2 bits) of the touched entries ...
+    __shared__ uint16_t s_el[8][128];      // ... and their entry index inside the warp's 128-entry span
+    __shared__ uint32_t s_w[8][128];       // new fp16 weights (half2 bits) by rank
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t i0 = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 8;
     const uint64_t warp_i0 = ((uint64_t)blockIdx.x * 256 + warp * 32) * 8;
@@ -730,8 +731,9 @@ __global__ void __launch_bounds__(256) nrc_optimizer_kernel(const __grid_constan
     const bool is_mlp = warp_i0 < a.n_mlp;                   // n_mlp is a multiple of 256: a warp never straddles the boundary
     union V8 { int4 v; __half h[8]; uint32_t u[4]; };
     V8 g, w, e;
-    g.v = make_int4(0, 0, 0, 0);
+    g.v = make_int4(0, 0, 0, 0); w.v = g.v; e.v = g.v;
     const float inv_scale = 1.0f / a.loss_scale;
+    if (in_range) e.v = *reinterpret_cast<const int4*>(a.ema16 + i0);
     if (is_mlp) {
         // network weights: every parameter is updated; gradient = fixed-order sum of the weight-gradient partials
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -740,47 +742,95 @@ __global__ void __launch_bounds__(256) nrc_optimizer_kernel(const __grid_constan
             const float4 p0 = p[0], p1 = p[1];
             acc[0] += p0.x; acc[1] += p0.y; acc[2] += p0.z; acc[3] += p0.w; acc[4] += p1.x; acc[5] += p1.y; acc[6] += p1.z; acc[7] += p1.w;
         }
-#pragma unroll
-        for (int j = 0; j < 8; j++) g.h[j] = __float2half_rn(acc[j]);      // tcnn keeps gradients in fp16 (trainer.h:322-336)
-        *reinterpret_cast<int4*>(a.grad16 + i0) = g.v;
-#pragma unroll
-        for (int j = 0; j < 8; j++) w.h[j] = adam_one(a, i0 + j, true, __half2float(g.h[j]) * inv_scale);
-        *reinterpret_cast<int4*>(a.w16 + i0) = w.v;
-    } else {
-        if (in_range) g.v = *reinterpret_cast<const int4*>(a.grad16 + i0);
-        uint32_t base = 0, my_rank[8];
-        bool mine[8];
+        float mw[8], m1[8], m2[8]; uint32_t st[8];
+        *reinterpret_cast<float4*>(mw) = *reinterpret_cast<const float4*>(a.master + i0); *reinterpret_cast<float4*>(mw + 4) = *reinterpret_cast<const float4*>(a.master + i0 + 4);
+        *reinterpret_cast<float4*>(m1) = *reinterpret_cast<const float4*>(a.m1 + i0); *reinterpret_cast<float4*>(m1 + 4) = *reinterpret_cast<const float4*>(a.m1 + i0 + 4);
+        *reinterpret_cast<float4*>(m2) = *reinterpret_cast<const float4*>(a.m2 + i0); *reinterpret_cast<float4*>(m2 + 4) = *reinterpret_cast<const float4*>(a.m2 + i0 + 4);
+        *reinterpret_cast<uint4*>(st) = *reinterpret_cast<const uint4*>(a.steps + i0); *reinterpret_cast<uint4*>(st + 4) = *reinterpret_cast<const uint4*>(a.steps + i0 + 4);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            mine[j] = __half2float(g.h[j]) != 0.0f;
+            g.h[j] = __float2half_rn(acc[j]);                              // tcnn keeps gradients in fp16 (trainer.h:322-336)
+            const float gradient = __half2float(g.h[j]) * inv_scale + a.l2_reg * mw[j];
+            mw[j] = adam_update(a, mw[j], m1[j], m2[j], st[j], gradient);
+            w.h[j] = __float2half_rn(mw[j]);
+        }
+        *reinterpret_cast<float4*>(a.master + i0) = *reinterpret_cast<float4*>(mw); *reinterpret_cast<float4*>(a.master + i0 + 4) = *reinterpret_cast<float4*>(mw + 4);
+        *reinterpret_cast<float4*>(a.m1 + i0) = *reinterpret_cast<float4*>(m1); *reinterpret_cast<float4*>(a.m1 + i0 + 4) = *reinterpret_cast<float4*>(m1 + 4);
+        *reinterpret_cast<float4*>(a.m2 + i0) = *reinterpret_cast<float4*>(m2); *reinterpret_cast<float4*>(a.m2 + i0 + 4) = *reinterpret_cast<float4*>(m2 + 4);
+        *reinterpret_cast<uint4*>(a.steps + i0) = *reinterpret_cast<uint4*>(st); *reinterpret_cast<uint4*>(a.steps + i0 + 4) = *reinterpret_cast<uint4*>(st + 4);
+        *reinterpret_cast<int4*>(a.grad16 + i0) = g.v;
+        *reinterpret_cast<int4*>(a.w16 + i0) = w.v;
+    } else {
+        if (in_range) { g.v = *reinterpret_cast<const int4*>(a.grad16 + i0); w.v = *reinterpret_cast<const int4*>(a.w16 + i0); }
+        uint32_t base = 0, my_rank[4];
+        bool mine[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            mine[j] = (g.u[j] & 0x7fff7fffu) != 0u;              // at least one of the entry's two gradients is non-zero (+-0 both skip)
             const uint32_t b = __ballot_sync(0xffffffffu, mine[j]);
             my_rank[j] = base + __popc(b & ((1u << lane) - 1));
             base += __popc(b);
         }
         if (base) {
 #pragma unroll
-            for (int j = 0; j < 8; j++)
-                if (mine[j]) { s_el[warp][my_rank[j]] = (uint16_t)(lane * 8 + j); s_g[warp][my_rank[j]] = g.h[j]; }
+            for (int j = 0; j < 4; j++)
+                if (mine[j]) { s_el[warp][my_rank[j]] = (uint16_t)(lane * 4 + j); s_g[warp][my_rank[j]] = g.u[j]; }
             __syncwarp();
+            GridAdamState* st0 = a.grid_state + ((warp_i0 - a.n_mlp) >> 1);
             for (uint32_t r = lane; r < base; r += 32) {
-                const uint64_t i = warp_i0 + s_el[warp][r];
-                a.w16[i] = adam_one(a, i, false, __half2float(s_g[warp][r]) * inv_scale);
+                float4* sp = reinterpret_cast<float4*>(st0 + s_el[warp][r]);
+                float4 s0 = sp[0];                                  // master.xy, m1.xy
+                float4 s1 = sp[1];                                  // m2.xy, steps.xy
+                const uint32_t gb = s_g[warp][r];
+                const __half2 gh = *reinterpret_cast<const __half2*>(&gb);
+                const float g0 = __low2float(gh), g1 = __high2float(gh);
+                uint32_t t0 = __float_as_uint(s1.z), t1 = __float_as_uint(s1.w);
+                if (g0 != 0.0f) s0.x = adam_update(a, s0.x, s0.z, s1.x, t0, g0 * inv_scale);
+                if (g1 != 0.0f) s0.y = adam_update(a, s0.y, s0.w, s1.y, t1, g1 * inv_scale);
+                s1.z = __uint_as_float(t0); s1.w = __uint_as_float(t1);
+                sp[0] = s0; sp[1] = s1;
+                s_w[warp][r] = tc05::pack_f16x2(s0.x, s0.y);
             }
             __syncwarp();
-            if (in_range && ((g.u[0] | g.u[1] | g.u[2] | g.u[3]) & 0x7fff7fffu)) *reinterpret_cast<int4*>(a.grad16 + i0) = make_int4(0, 0, 0, 0);   // consumed
+            bool any = false;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (mine[j]) {
+                    // a feature whose own gradient is zero keeps its fp16 weight bit for bit (its master did not move)
+                    const uint32_t nw = s_w[warp][my_rank[j]];
+                    const uint32_t keep_lo = (g.u[j] & 0x00007fffu) ? 0u : 0x0000ffffu, keep_hi = (g.u[j] & 0x7fff0000u) ? 0u : 0xffff0000u;
+                    const uint32_t keep = keep_lo | keep_hi;
+                    w.u[j] = (w.u[j] & keep) | (nw & ~keep);
+                    any = true;
+                }
+            if (any) {
+                *reinterpret_cast<int4*>(a.w16 + i0) = w.v;
+                *reinterpret_cast<int4*>(a.grad16 + i0) = make_int4(0, 0, 0, 0);   // consumed
+            }
         }
-        if (in_range) w.v = *reinterpret_cast<const int4*>(a.w16 + i0);
     }
     if (!in_range) return;
-    e.v = *reinterpret_cast<const int4*>(a.ema16 + i0);
-    const float k_old = a.ema_decay * a.ema_debias_old, k_new = 1 - a.ema_decay;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         const float filtered = (__half2float(e.h[j]) * a.ema_decay * a.ema_debias_old + __half2float(w.h[j]) * (1 - a.ema_decay)) * a.ema_debias_new;
         e.h[j] = __float2half_rn(filtered);
     }
-    (void)k_old; (void)k_new;
     *reinterpret_cast<int4*>(a.ema16 + i0) = e.v;
+}
+
+// (un)packing between the tcnn parameter order and the per-entry Adam records (nrc_get_params / nrc_set_params_fp32)
+__global__ void __launch_bounds__(256) nrc_grid_state_scatter_kernel(GridAdamState* st, uint64_t n_entries, int field, const float* __restrict__ src) {
+    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_entries) return;
+    float* f = reinterpret_cast<float*>(st + i) + 2 * field;
+    f[0] = src[2 * i]; f[1] = src[2 * i + 1];
+}
+__global__ void __launch_bounds__(256) nrc_grid_state_gather_kernel(const GridAdamState* st, uint64_t n_entries, int field, float* __restrict__ dst) {
+    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_entries) return;
+    const float* f = reinterpret_cast<const float*>(st + i) + 2 * field;
+    if (field == 3) { dst[2 * i] = (float)__float_as_uint(f[0]); dst[2 * i + 1] = (float)__float_as_uint(f[1]); }
+    else { dst[2 * i] = f[0]; dst[2 * i + 1] = f[1]; }
 }
 
 }  // namespace nrchpm

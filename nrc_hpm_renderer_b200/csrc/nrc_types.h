@@ -26,4 +26,14 @@ struct EncParams {
     uint32_t level_hash[kMaxLevels];
 };
 
+// Adam state of ONE hash-grid entry (two fp16 features): fp32 master weights, first / second moments and the per-parameter
+// step counters (adam.h:48-121 keeps four separate arrays).  32 bytes = one DRAM / L2 sector, so the optimizer touches one
+// sector per updated entry instead of four.
+struct alignas(32) GridAdamState {
+    float master[2];
+    float m1[2];
+    float m2[2];
+    uint32_t steps[2];
+};
+
 }  // namespace nrchpm
