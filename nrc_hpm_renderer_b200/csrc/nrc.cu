@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 #include <vector>
@@ -300,7 +301,13 @@ void NrcCache::setup_kernels() {
         NRCHPM_CUDA(cudaFuncSetAttribute(nrc_forward_kernel<IN_W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem_bytes<IN_W>(H)));
         NRCHPM_CUDA(cudaFuncSetAttribute(nrc_backward_kernel<IN_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem_bytes<IN_W>(H)));
         NRCHPM_CUDA(cudaFuncSetAttribute(nrc_dw_kernel<IN_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDwSmemBytes));
+        NRCHPM_CUDA(cudaFuncSetAttribute(nrc_forward2_kernel<IN_W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd2_smem_bytes<IN_W>(H, 3)));
+        NRCHPM_CUDA(cudaFuncSetAttribute(nrc_forward2_kernel<IN_W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd2_smem_bytes<IN_W>(H, 1)));
+        NRCHPM_CUDA(cudaFuncSetAttribute(nrc_backward2_kernel<IN_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd2_smem_bytes<IN_W>(H)));
     });
+    // tuning knobs (experiments only; the defaults are the measured best)
+    if (const char* v = std::getenv("NRCHPM_INFER_GROUPS")) infer_groups_ = std::max(0, std::min(3, std::atoi(v)));
+    if (const char* v = std::getenv("NRCHPM_TRAIN_GROUPS")) train_groups_ = std::max(0, std::min(1, std::atoi(v)));
 }
 
 void NrcCache::encode(const float* d_in, uint32_t n, bool use_ema, void* d_out_half, cudaStream_t s) {
@@ -316,6 +323,15 @@ void NrcCache::inference(const float* d_in, float* d_out, uint32_t n, bool use_e
     a.in = d_in; a.indices = d_indices; a.d_count = d_count; a.n = n; a.out = d_out;
     const uint32_t tiles = (n + kTile - 1) / kTile;
     uint32_t grid, threads;
+    if (infer_groups_ > 0) {
+        const uint32_t g = (uint32_t)infer_groups_;
+        grid = std::min<uint32_t>((tiles + g - 1) / g, (uint32_t)sm_count_);
+        NRC_DISPATCH_INW(enc_.in_w, {
+            nrc_forward2_kernel<IN_W, false><<<grid, g * kGroupThreads, fwd2_smem_bytes<IN_W>(cfg_.n_hidden_layers, (int)g), s>>>(a);
+        });
+        check_launch("nrc_forward2_kernel<infer>");
+        return;
+    }
     launch_shape(tiles, grid, threads);
     NRC_DISPATCH_INW(enc_.in_w, {
         nrc_forward_kernel<IN_W, false><<<grid, threads, fwd_smem_bytes<IN_W>(cfg_.n_hidden_layers), s>>>(a);
@@ -358,7 +374,12 @@ void NrcCache::training_step(const float* d_in, const float* d_target, uint32_t 
         a.in = d_in; a.n = B; a.target = d_target;
         a.x16 = x16_.ptr; a.acts = acts_.ptr; a.out16 = out16_.ptr; a.dout16 = dout16_.ptr; a.loss_partials = loss_partials_.ptr;
         a.loss_scale = cfg_.loss_scale;
-        NRC_DISPATCH_INW(enc_.in_w, { nrc_forward_kernel<IN_W, true><<<grid, threads, fwd_smem_bytes<IN_W>(H), s>>>(a); });
+        if (train_groups_ > 0) {
+            const uint32_t g = (uint32_t)train_groups_, grid2 = std::min<uint32_t>((tiles + g - 1) / g, (uint32_t)sm_count_ * 2);
+            NRC_DISPATCH_INW(enc_.in_w, { nrc_forward2_kernel<IN_W, true><<<grid2, g * kGroupThreads, fwd2_smem_bytes<IN_W>(H, (int)g), s>>>(a); });
+        } else {
+            NRC_DISPATCH_INW(enc_.in_w, { nrc_forward_kernel<IN_W, true><<<grid, threads, fwd_smem_bytes<IN_W>(H), s>>>(a); });
+        }
         check_launch("nrc_forward_kernel<train>");
     }
     {
@@ -369,7 +390,12 @@ void NrcCache::training_step(const float* d_in, const float* d_target, uint32_t 
         a.dx16 = (n_grid_ && keep_dx_) ? dx16_.ptr : nullptr;
         a.grid_grad = n_grid_ ? grad16_.ptr + n_mlp_ : nullptr;
         a.loss_partials = loss_partials_.ptr; a.loss_out = loss_dev_.ptr; a.n_loss_partials = tiles;
-        NRC_DISPATCH_INW(enc_.in_w, { nrc_backward_kernel<IN_W><<<grid, threads, bwd_smem_bytes<IN_W>(H), s>>>(a); });
+        if (train_groups_ > 0) {
+            const uint32_t g = (uint32_t)train_groups_, grid2 = std::min<uint32_t>((tiles + g - 1) / g, (uint32_t)sm_count_ * 2);
+            NRC_DISPATCH_INW(enc_.in_w, { nrc_backward2_kernel<IN_W><<<grid2, g * kGroupThreads, bwd2_smem_bytes<IN_W>(H), s>>>(a); });
+        } else {
+            NRC_DISPATCH_INW(enc_.in_w, { nrc_backward_kernel<IN_W><<<grid, threads, bwd_smem_bytes<IN_W>(H), s>>>(a); });
+        }
         check_launch("nrc_backward_kernel");
         grid_grad_dirty_ = n_grid_ != 0;
     }

@@ -75,6 +75,7 @@ private:
     EncParams enc_;
     size_t n_mlp_ = 0, n_grid_ = 0, n_params_ = 0;
     int sm_count_ = 148;
+    int infer_groups_ = 0, train_groups_ = 1;      // 256-thread groups per CTA of the two-threads-per-record kernels (0: one-thread kernels)
     DeviceBuffer<float> master_, m1_, m2_, loss_dev_, loss_partials_, dw_partials_, mlp_grad_f32_;
     DeviceBuffer<__half> w16_, ema16_, grad16_, x16_, acts_, dacts_, out16_, dout16_, dx16_;
     DeviceBuffer<uint32_t> steps_;

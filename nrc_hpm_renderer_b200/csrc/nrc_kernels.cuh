@@ -64,14 +64,13 @@ __device__ __forceinline__ void grid_level_cell(const EncParams& e, int l, float
 }
 
 // put(k, half) / put2(k_even, half2) receive feature k of this record.
-template <class Put>
-__device__ __forceinline__ void encode_record(const EncParams& e, const __half2* __restrict__ grid, float x0, float x1, float x2,
-                                              float th, float ph, Put& put) {
-    const __half one = __float2half_rn(1.0f);
-    // ---- position
+// Position features: hash-grid levels [l_begin, l_end) -- the whole encoding for the other (parameter-free) encoders.
+template <int UNROLL = 2, class Put>
+__device__ __forceinline__ void encode_position(const EncParams& e, const __half2* __restrict__ grid, float x0, float x1, float x2,
+                                                int l_begin, int l_end, Put& put) {
     if (e.pos_enc == POS_HASHGRID) {
-#pragma unroll 2
-        for (int l = 0; l < e.n_levels; l++) {
+#pragma unroll UNROLL
+        for (int l = l_begin; l < l_end; l++) {
             GridLevel c;
             grid_level_cell(e, l, x0, x1, x2, c);
             const __half2* base = grid + e.level_offset[l];
@@ -126,7 +125,12 @@ __device__ __forceinline__ void encode_record(const EncParams& e, const __half2*
                 put.put((d * e.n_freq_pos + f) * 2 + 1, __float2half_rn(__sinf(x + PI / 2)));
             }
     }
-    // ---- direction
+}
+
+// Direction features and the padding columns (one thread does both: the padding overwrites direction columns under Q6).
+template <class Put>
+__device__ __forceinline__ void encode_direction_pad(const EncParams& e, float th, float ph, Put& put) {
+    const __half one = __float2half_rn(1.0f);
     const int o = e.dir_off;
     const float ds[2] = {th, ph};
     if (e.dir_enc == DIR_ONEBLOB) {
@@ -176,6 +180,13 @@ __device__ __forceinline__ void encode_record(const EncParams& e, const __half2*
     }
 }
 
+template <class Put>
+__device__ __forceinline__ void encode_record(const EncParams& e, const __half2* __restrict__ grid, float x0, float x1, float x2,
+                                              float th, float ph, Put& put) {
+    encode_position(e, grid, x0, x1, x2, 0, e.n_levels, put);
+    encode_direction_pad(e, th, ph, put);
+}
+
 // K-major canonical (no swizzle) tile in shared memory: this thread's row
 struct SmemRowPut {
     uint8_t* row;   // tile + (r/8)*SBO + (r%8)*16
@@ -216,6 +227,28 @@ __device__ __forceinline__ void copy_weights_mnmajor(uint8_t* dst, const __half*
         const int o = c / i8n, i8 = c - o * i8n;
         *reinterpret_cast<int4*>(dst + i8 * sbo + (o & 7) * 16 + (o >> 3) * 128) = *reinterpret_cast<const int4*>(src + (size_t)o * I + i8 * 8);
     }
+}
+
+// the same two layouts, copied with cp.async (the caller waits: cp_async_wait_all + fence.proxy.async before the first MMA)
+__device__ __forceinline__ void copy_weights_kmajor_async(uint8_t* dst, const __half* __restrict__ src, int rows, int K, int tid, int nthreads) {
+    const int k8n = K >> 3, chunks = rows * k8n;
+    for (int c = tid; c < chunks; c += nthreads) {
+        const int n = c / k8n, k8 = c - n * k8n;
+        tc05::cp_async16(dst + (n >> 3) * (k8n * 128) + k8 * 128 + (n & 7) * 16, src + (size_t)n * K + k8 * 8);
+    }
+}
+__device__ __forceinline__ void copy_weights_mnmajor_async(uint8_t* dst, const __half* __restrict__ src, int O, int I, int tid, int nthreads) {
+    const int i8n = I >> 3, chunks = O * i8n;
+    const int sbo = (O >> 3) * 128;
+    for (int c = tid; c < chunks; c += nthreads) {
+        const int o = c / i8n, i8 = c - o * i8n;
+        tc05::cp_async16(dst + i8 * sbo + (o & 7) * 16 + (o >> 3) * 128, src + (size_t)o * I + i8 * 8);
+    }
+}
+// fire-and-forget fp16x2 reduction.  (atomicAdd(__half2*) on a generic pointer compiles to ATOM with a predicate result plus
+// shared / local fall-back paths, and every call then waits for the round trip to L2.)
+__device__ __forceinline__ void red_add_f16x2(__half2* addr, __half2 v) {
+    asm volatile("red.global.add.noftz.f16x2 [%0], %1;" ::"l"(__cvta_generic_to_global(addr)), "r"(*reinterpret_cast<const uint32_t*>(&v)) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------- forward
@@ -563,7 +596,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) nrc_backward_kernel(const __gr
                     grid_level_cell(a.enc, l, x0, x1, x2, c);
                     __half2* base = gg + a.enc.level_offset[l];
 #pragma unroll
-                    for (int k = 0; k < 8; k++) atomicAdd(base + c.idx[k], __hmul2(__half2half2(__float2half_rn(c.w[k])), g));
+                    for (int k = 0; k < 8; k++) red_add_f16x2(base + c.idx[k], __hmul2(__half2half2(__float2half_rn(c.w[k])), g));
                 }
             }
         }
@@ -571,6 +604,358 @@ __global__ void __launch_bounds__(kFwdThreads, 2) nrc_backward_kernel(const __gr
     fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base_s, 2 * kColsPerWg);
+}
+
+// ---------------------------------------------------------------------------------------------- two threads per record
+// Second generation of the forward / backward kernels: a tile of 128 records is owned by a GROUP of 256 threads.  Warps w and
+// w + 4 of a group share one TMEM lane quadrant (= the same 32 records) and split the per-record work: hash-grid levels
+// [0, L/2) vs [L/2, L) + direction encoding, accumulator columns [0, 32) vs [32, 64) in every epilogue, and the gradient
+// scatter by levels again.  The dependent chain per tile (gather rounds, tcgen05.ld -> cvt -> tcgen05.st per layer, atomics)
+// is half as long and twice as many warps are in flight per tile -- what the latency-bound 128-tile training batch needs.
+// A CTA carries blockDim.x / 256 groups (tiles in flight); one CTA per SM.
+constexpr int kGroupThreads = 256;
+
+template <int IN_W>
+__host__ __device__ constexpr size_t fwd2_smem_bytes(int n_hidden, int groups) {
+    return (size_t)IN_W * 128 + (size_t)(n_hidden - 1) * 8192 + 2048 + (size_t)groups * IN_W * 256;
+}
+__host__ __device__ constexpr uint32_t tmem_cols_for_groups(int groups) { return groups <= 1 ? 128u : groups == 2 ? 256u : 512u; }
+
+template <int IN_W, bool TRAIN>
+__global__ void __launch_bounds__(TRAIN ? 256 : 768, TRAIN ? 2 : 1) nrc_forward2_kernel(const __grid_constant__ FwdArgs a) {
+    using namespace tc05;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t mbar[4], wbar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float loss_red[4][4];
+    const int tid = threadIdx.x, grp = tid >> 8, warp = tid >> 5, lane = tid & 31;
+    const int quad = warp & 3, half = (warp >> 2) & 1, r = quad * 32 + lane;
+    const int nthreads = blockDim.x, ngrp = nthreads >> 8;
+    const int H = a.n_hidden;
+    uint8_t* w0_s = smem;
+    uint8_t* wh_s = w0_s + IN_W * 128;
+    uint8_t* wo_s = wh_s + (H - 1) * 8192;
+    uint8_t* x_s = wo_s + 2048 + grp * (IN_W * 256);
+
+    if (warp == 0) { tmem_alloc(&tmem_base_s, tmem_cols_for_groups(ngrp)); tmem_relinquish(); }
+    if (tid == 0) { for (int g = 0; g < ngrp; g++) mbar_init(&mbar[g], 1); mbar_init(&wbar, nthreads); fence_mbar_init(); }
+    // the weights travel to shared memory asynchronously while the first tile is encoded; every thread arrives on `wbar` once its
+    // copies have landed (and are visible to the tensor core's proxy), the group leaders wait on it before their first MMA
+    copy_weights_kmajor_async(w0_s, a.params, kWidth, IN_W, tid, nthreads);
+    for (int l = 1; l < H; l++) copy_weights_kmajor_async(wh_s + (l - 1) * 8192, a.params + IN_W * kWidth + (l - 1) * kWidth * kWidth, kWidth, kWidth, tid, nthreads);
+    copy_weights_kmajor_async(wo_s, a.params + IN_W * kWidth + (H - 1) * kWidth * kWidth, kOutPad, kWidth, tid, nthreads);
+    bool weights_pending = true;
+    fence_before();
+    __syncthreads();
+    fence_after();
+
+    const uint32_t tD = tmem_base_s + grp * kColsPerWg + kColD, tA = tmem_base_s + grp * kColsPerWg + kColA;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const uint32_t idesc64 = make_idesc_f16(128, 64), idesc16 = make_idesc_f16(128, 16);
+    const uint32_t x_addr = smem_u32(x_s), w0_addr = smem_u32(w0_s), wh_addr = smem_u32(wh_s), wo_addr = smem_u32(wo_s);
+    const __half2* grid = reinterpret_cast<const __half2*>(a.params + a.n_mlp);
+    uint64_t* bar = &mbar[grp];
+    uint32_t phase = 0;
+    const bool leader = (tid & 255) == 0;
+    const bool hashgrid = a.enc.pos_enc == POS_HASHGRID;
+    const int l_split = hashgrid ? (a.enc.n_levels + 1) / 2 : a.enc.n_levels;
+
+    uint32_t n = a.n;
+    if (a.d_count) n = min(n, *a.d_count);
+    const uint32_t n_tiles = (n + kTile - 1) / kTile;
+
+    for (uint32_t tile = blockIdx.x * ngrp + grp; tile < n_tiles; tile += gridDim.x * ngrp) {
+        const uint32_t row = tile * kTile + r;
+        const bool valid = row < n;
+        uint32_t rec = 0;
+        float x0 = 0, x1 = 0, x2 = 0, th = 0, ph = 0;
+        if (valid) {
+            rec = a.indices ? a.indices[row] : row;
+            const float* p = a.in + 5 * (size_t)rec;
+            x0 = p[0]; x1 = p[1]; x2 = p[2]; th = p[3]; ph = p[4];
+        }
+        uint8_t* my_row = x_s + (r >> 3) * (IN_W * 16) + (r & 7) * 16;
+        SmemRowPut put{my_row};
+        {   // one call site (code size: each CTA runs this once in the 128-tile training batch, instruction fetch is cold)
+            const int lb = half == 0 ? 0 : l_split, le = (half == 0 || !hashgrid) ? l_split : a.enc.n_levels;
+            if (half == 0 || hashgrid) encode_position<TRAIN ? 4 : 2>(a.enc, grid, x0, x1, x2, lb, le, put);
+            if (half == 1) encode_direction_pad(a.enc, th, ph, put);
+        }
+        if (weights_pending) { cp_async_wait_all(); fence_proxy_async_smem(); mbar_arrive(&wbar); }
+        fence_proxy_async_smem();
+        fence_before();
+        named_bar_sync(1 + grp, kGroupThreads);
+        if (leader) {
+            if (weights_pending) mbar_wait(&wbar, 0);
+            fence_after();
+#pragma unroll
+            for (int s = 0; s < IN_W / 16; s++)
+                mma_f16_ss(tD, make_smem_desc(x_addr + s * 256, 128, IN_W * 16), make_smem_desc(w0_addr + s * 256, 128, IN_W * 16), idesc64, s > 0);
+            mma_commit(bar);
+        }
+        weights_pending = false;
+        if (TRAIN) {
+            int4* dst = reinterpret_cast<int4*>(a.x16 + (size_t)row * IN_W);
+#pragma unroll
+            for (int c = 0; c < IN_W / 16; c++) dst[half * (IN_W / 16) + c] = *reinterpret_cast<const int4*>(my_row + (half * (IN_W / 16) + c) * 128);
+        }
+        mbar_wait(bar, phase); phase ^= 1;
+        fence_after();
+
+        for (int l = 0; l < H; l++) {
+            // epilogue of hidden layer l, this thread's 32 columns: ReLU -> fp16 -> A operand of the next layer
+            uint32_t acc[32], p[16];
+            tmem_ld32(tD + lane_base + half * 32, acc);
+            wait_ld();
+            if (l == 0) {
+                // tcnn's ReLU is max(x, 0) in fp16, which maps NaN to 0 (NaN features reach layer 0 through the
+                // reference's phi = acos(>1)); cvt.relu would keep the NaN.  Later layers cannot see one.
+                const __half2 zero2 = __float2half2_rn(0.0f);
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    uint32_t v = pack_f16x2(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
+                    __half2 m = __hmax2(*reinterpret_cast<__half2*>(&v), zero2);
+                    p[j] = *reinterpret_cast<uint32_t*>(&m);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; j++) p[j] = pack_relu_f16x2(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
+            }
+            tmem_st16(tA + lane_base + half * 16, p);
+            if (TRAIN) {
+                int4* dst = reinterpret_cast<int4*>(a.acts + ((size_t)l * a.n + row) * kWidth + half * 32);
+#pragma unroll
+                for (int c = 0; c < 4; c++) dst[c] = make_int4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
+            }
+            wait_st();
+            fence_before();
+            named_bar_sync(1 + grp, kGroupThreads);
+            if (leader) {
+                fence_after();
+                if (l < H - 1) {
+#pragma unroll
+                    for (int s = 0; s < 4; s++) mma_f16_ts(tD, tA + s * 8, make_smem_desc(wh_addr + l * 8192 + s * 256, 128, 1024), idesc64, s > 0);
+                } else {
+#pragma unroll
+                    for (int s = 0; s < 4; s++) mma_f16_ts(tD, tA + s * 8, make_smem_desc(wo_addr + s * 256, 128, 1024), idesc16, s > 0);
+                }
+                mma_commit(bar);
+            }
+            mbar_wait(bar, phase); phase ^= 1;
+            fence_after();
+        }
+        // output layer (16 accumulator columns): fp16 like tcnn's network output, then float (common_device.h:990-999)
+        float loss = 0;
+        if (half == 0) {
+            uint32_t o[16];
+            tmem_ld16(tD + lane_base, o);
+            wait_ld();
+            if (!TRAIN) {
+                if (valid) {
+                    float* dst = a.out + 3 * (size_t)rec;
+#pragma unroll
+                    for (int k = 0; k < 3; k++) dst[k] = __half2float(__float2half_rn(__uint_as_float(o[k])));
+                }
+            } else {
+                uint32_t ph16[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) ph16[j] = pack_f16x2(__uint_as_float(o[2 * j]), __uint_as_float(o[2 * j + 1]));
+                int4* od = reinterpret_cast<int4*>(a.out16 + (size_t)row * kOutPad);
+                od[0] = make_int4(ph16[0], ph16[1], ph16[2], ph16[3]);
+                od[1] = make_int4(ph16[4], ph16[5], ph16[6], ph16[7]);
+                // RelativeL2Luminance (relative_l2_luminance.h:40-88); n_total = batch * 3 (padded dims contribute nothing)
+                float pr[3];
+#pragma unroll
+                for (int k = 0; k < 3; k++) pr[k] = __half2float(__float2half_rn(__uint_as_float(o[k])));
+                const float n_total = (float)(a.n * 3u);
+                const float lum = 0.299f * pr[0] + 0.587f * pr[1] + 0.114f * pr[2];
+                const float denom = lum * lum + 0.01f;
+                float gk[3];
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const float diff = pr[k] - a.target[3 * (size_t)row + k];
+                    loss += diff * diff / denom / n_total;
+                    gk[k] = a.loss_scale * (2 * diff / denom) / n_total;
+                }
+                int4* gd = reinterpret_cast<int4*>(a.dout16 + (size_t)row * kOutPad);
+                gd[0] = make_int4(pack_f16x2(gk[0], gk[1]), pack_f16x2(gk[2], 0.0f), 0, 0);
+                gd[1] = make_int4(0, 0, 0, 0);
+                // deterministic per-tile loss sum: warp shuffle tree, then 4 partials added in order
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, s);
+                if (lane == 0) loss_red[grp][quad] = loss;
+            }
+        }
+        if (TRAIN) {
+            named_bar_sync(1 + grp, kGroupThreads);
+            if (leader) a.loss_partials[tile] = ((loss_red[grp][0] + loss_red[grp][1]) + loss_red[grp][2]) + loss_red[grp][3];
+        }
+    }
+    if (weights_pending) { cp_async_wait_all(); mbar_arrive(&wbar); }     // a group without tiles
+    fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base_s, tmem_cols_for_groups(ngrp));
+}
+
+template <int IN_W>
+__host__ __device__ constexpr size_t bwd2_smem_bytes(int n_hidden) {
+    return (size_t)IN_W * 128 + (size_t)(n_hidden - 1) * 8192 + 2048;
+}
+
+template <int IN_W>
+__global__ void __launch_bounds__(256, 2) nrc_backward2_kernel(const __grid_constant__ BwdArgs a) {
+    using namespace tc05;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t mbar[4], wbar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, grp = tid >> 8, warp = tid >> 5, lane = tid & 31;
+    const int quad = warp & 3, half = (warp >> 2) & 1, r = quad * 32 + lane;
+    const int nthreads = blockDim.x, ngrp = nthreads >> 8;
+    const int H = a.n_hidden;
+    uint8_t* w0_s = smem;
+    uint8_t* wh_s = w0_s + IN_W * 128;
+    uint8_t* wo_s = wh_s + (H - 1) * 8192;
+
+    if (warp == 0) { tmem_alloc(&tmem_base_s, tmem_cols_for_groups(ngrp)); tmem_relinquish(); }
+    if (tid == 0) { for (int g = 0; g < ngrp; g++) mbar_init(&mbar[g], 1); mbar_init(&wbar, nthreads); fence_mbar_init(); }
+    if (blockIdx.x == 0 && warp == 1 && a.loss_out) {     // Trainer::loss (trainer.h:205-207): fixed-order sum of the tile partials
+        // lanes read in parallel, lane 0 adds in tile order (deterministic)
+        float s = 0;
+        for (uint32_t i0 = 0; i0 < a.n_loss_partials; i0 += 32) {
+            const float v = (i0 + lane < a.n_loss_partials) ? a.loss_partials[i0 + lane] : 0.0f;
+#pragma unroll
+            for (int j = 0; j < 32; j++) { const float vj = __shfl_sync(0xffffffffu, v, j); if (i0 + j < a.n_loss_partials) s += vj; }
+        }
+        if (lane == 0) *a.loss_out = s;
+    }
+    copy_weights_mnmajor_async(wo_s, a.params + IN_W * kWidth + (H - 1) * kWidth * kWidth, kOutPad, kWidth, tid, nthreads);
+    for (int l = H - 1; l >= 1; l--) copy_weights_mnmajor_async(wh_s + (l - 1) * 8192, a.params + IN_W * kWidth + (l - 1) * kWidth * kWidth, kWidth, kWidth, tid, nthreads);
+    copy_weights_mnmajor_async(w0_s, a.params, kWidth, IN_W, tid, nthreads);
+    bool weights_pending = true;
+    fence_before();
+    __syncthreads();
+    fence_after();
+
+    const uint32_t tD = tmem_base_s + grp * kColsPerWg + kColD, tA = tmem_base_s + grp * kColsPerWg + kColA;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const uint32_t idesc64 = make_idesc_f16(128, 64, 0, 1), idescx = make_idesc_f16(128, IN_W, 0, 1);
+    const uint32_t w0_addr = smem_u32(w0_s), wh_addr = smem_u32(wh_s), wo_addr = smem_u32(wo_s);
+    uint64_t* bar = &mbar[grp];
+    uint32_t phase = 0;
+    const bool leader = (tid & 255) == 0;
+    const uint32_t n_tiles = a.n / kTile;
+    const bool scatter = a.grid_grad && a.enc.pos_enc == POS_HASHGRID;
+    const int l_split = (a.enc.n_levels + 1) / 2;
+
+    for (uint32_t tile = blockIdx.x * ngrp + grp; tile < n_tiles; tile += gridDim.x * ngrp) {
+        const uint32_t row = tile * kTile + r;
+        // requested early, consumed late: the record position (gradient scatter) and the last layer's activations (ReLU mask)
+        float x0 = 0, x1 = 0, x2 = 0;
+        if (scatter) { const float* rp = a.in + 5 * (size_t)row; x0 = rp[0]; x1 = rp[1]; x2 = rp[2]; }
+        int4 av[4];
+        {
+            const int4* ap = reinterpret_cast<const int4*>(a.acts + ((size_t)(H - 1) * a.n + row) * kWidth + half * 32);
+#pragma unroll
+            for (int c = 0; c < 4; c++) av[c] = ap[c];
+        }
+        if (half == 0) {   // dL/doutput row -> A operand (K = 16)
+            const int4* src = reinterpret_cast<const int4*>(a.dout16 + (size_t)row * kOutPad);
+            const int4 v0 = src[0], v1 = src[1];
+            uint32_t p[8] = {(uint32_t)v0.x, (uint32_t)v0.y, (uint32_t)v0.z, (uint32_t)v0.w, (uint32_t)v1.x, (uint32_t)v1.y, (uint32_t)v1.z, (uint32_t)v1.w};
+            tmem_st8(tA + lane_base, p);
+        }
+        wait_st();
+        if (weights_pending) { cp_async_wait_all(); fence_proxy_async_smem(); mbar_arrive(&wbar); }
+        fence_before();
+        named_bar_sync(1 + grp, kGroupThreads);
+        if (leader) {
+            if (weights_pending) mbar_wait(&wbar, 0);
+            fence_after();
+            mma_f16_ts(tD, tA, make_smem_desc(wo_addr, 128, 256), idesc64, 0);
+            mma_commit(bar);
+        }
+        weights_pending = false;
+        mbar_wait(bar, phase); phase ^= 1;
+        fence_after();
+
+        for (int l = H - 1; l >= 0; l--) {
+            uint32_t acc[32], p[16];
+            tmem_ld32(tD + lane_base + half * 32, acc);
+            wait_ld();
+            const uint32_t* aw = reinterpret_cast<const uint32_t*>(av);
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const float lo = (aw[j] & 0x0000ffffu) ? __uint_as_float(acc[2 * j]) : 0.0f;
+                const float hi = (aw[j] & 0xffff0000u) ? __uint_as_float(acc[2 * j + 1]) : 0.0f;
+                p[j] = pack_f16x2(lo, hi);
+            }
+            if (l > 0) {   // next layer's mask: in flight while the MMA below runs
+                const int4* ap = reinterpret_cast<const int4*>(a.acts + ((size_t)(l - 1) * a.n + row) * kWidth + half * 32);
+#pragma unroll
+                for (int c = 0; c < 4; c++) av[c] = ap[c];
+            }
+            tmem_st16(tA + lane_base + half * 16, p);
+            int4* dp = reinterpret_cast<int4*>(a.dacts + ((size_t)l * a.n + row) * kWidth + half * 32);
+#pragma unroll
+            for (int c = 0; c < 4; c++) dp[c] = make_int4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
+            if (l == 0 && !a.need_dx) break;
+            wait_st();
+            fence_before();
+            named_bar_sync(1 + grp, kGroupThreads);
+            if (leader) {
+                fence_after();
+                if (l > 0) {
+#pragma unroll
+                    for (int s = 0; s < 4; s++) mma_f16_ts(tD, tA + s * 8, make_smem_desc(wh_addr + (l - 1) * 8192 + s * 256, 128, 1024), idesc64, s > 0);
+                } else {
+#pragma unroll
+                    for (int s = 0; s < 4; s++) mma_f16_ts(tD, tA + s * 8, make_smem_desc(w0_addr + s * 256, 128, 1024), idescx, s > 0);
+                }
+                mma_commit(bar);
+            }
+            mbar_wait(bar, phase); phase ^= 1;
+            fence_after();
+        }
+        if (a.need_dx) {
+            if (a.dx16) {
+                // dL/d(network input): fp16 like tcnn's fc_multiply output (fully_fused_mlp.cu:832-835); this thread's half of the row
+                uint32_t* dst = reinterpret_cast<uint32_t*>(a.dx16 + (size_t)row * IN_W);
+#pragma unroll
+                for (int c = 0; c < IN_W / 2; c += 8) {
+                    uint32_t t[8];
+                    tmem_ld8(tD + lane_base + half * (IN_W / 2) + c, t);
+                    wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 4; j++) dst[(half * (IN_W / 2) + c) / 2 + j] = pack_f16x2(__uint_as_float(t[2 * j]), __uint_as_float(t[2 * j + 1]));
+                }
+            }
+            if (scatter) {
+                // kernel_grid_backward (grid.h:215-320): (half)weight * grad, fp16x2 atomics; levels split between the two halves.
+                // The level loop stays rolled (the gradient pair of level l is read from TMEM columns 2l, 2l+1): unrolled 16 x 8
+                // corners the kernel spent 40 % of its issue slots waiting for instruction fetch.
+                __half2* gg = reinterpret_cast<__half2*>(a.grid_grad);
+                const int lb = half == 0 ? 0 : l_split, le = half == 0 ? l_split : a.enc.n_levels;
+#pragma unroll 1
+                for (int l = lb; l < le; l++) {
+                    uint32_t t[2];
+                    tmem_ld2(tD + lane_base + 2 * l, t);
+                    wait_ld();
+                    const uint32_t gp = pack_f16x2(__uint_as_float(t[0]), __uint_as_float(t[1]));
+                    const __half2 g = *reinterpret_cast<const __half2*>(&gp);
+                    GridLevel c;
+                    grid_level_cell(a.enc, l, x0, x1, x2, c);
+                    __half2* base = gg + a.enc.level_offset[l];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) red_add_f16x2(base + c.idx[k], __hmul2(__half2half2(__float2half_rn(c.w[k])), g));
+                }
+            }
+            // (every thread's reads of tD are complete -- wait::ld -- before it reaches the next tile's first barrier)
+        }
+    }
+    if (weights_pending) { cp_async_wait_all(); mbar_arrive(&wbar); }     // a group without tiles
+    fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base_s, tmem_cols_for_groups(ngrp));
 }
 
 // ---------------------------------------------------------------------------------------------- weight gradients

@@ -1,0 +1,52 @@
+"""Kernel-variant timing on one B200 (CUDA events, inputs rotated through > L2): inference launch and training step under the
+NRCHPM_INFER_GROUPS / NRCHPM_TRAIN_GROUPS knobs of csrc/nrc.cu.  Development tool, not part of the product path."""
+import os, sys, json
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from bench import synth_records, N_INFER, TRAIN_BATCH
+from nrc_hpm_renderer_b200 import AppConfig
+from nrc_hpm_renderer_b200.nrc import NeuralRadianceCache
+
+def run(infer_groups, train_groups, ref_out=None, n_infer=N_INFER, iters=20):
+    os.environ["NRCHPM_INFER_GROUPS"] = str(infer_groups)
+    os.environ["NRCHPM_TRAIN_GROUPS"] = str(train_groups)
+    app = AppConfig.default()
+    nrc = NeuralRadianceCache(app)
+    st = torch.cuda.current_stream(); sp = st.cuda_stream
+    rng = np.random.default_rng(1337)
+    d_in = [torch.from_numpy(synth_records(rng, n_infer)).cuda() for _ in range(4)]
+    d_out = [torch.empty((n_infer, 3), dtype=torch.float32, device="cuda") for _ in range(4)]
+    tin = [torch.from_numpy(synth_records(rng, TRAIN_BATCH)).cuda() for _ in range(8)]
+    tgt = [torch.from_numpy((rng.random((TRAIN_BATCH, 3), dtype=np.float32) * 2).astype(np.float32)).cuda() for _ in range(8)]
+    losses = []
+    for i in range(8):
+        nrc.training_step(tin[i], tgt[i], TRAIN_BATCH, True, sp); losses.append(nrc.GetLoss())
+    for i in range(4):
+        nrc.inference(d_in[i], d_out[i], n_infer, True, sp)
+    torch.cuda.synchronize()
+    out0 = d_out[0].cpu().numpy()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for i in range(iters):
+        nrc.inference(d_in[i % 4], d_out[i % 4], n_infer, True, sp)
+    e1.record(st); torch.cuda.synchronize()
+    t_inf = e0.elapsed_time(e1) / iters
+    e0.record(st)
+    for i in range(200):
+        nrc.training_step(tin[i % 8], tgt[i % 8], TRAIN_BATCH, True, sp)
+    e1.record(st); torch.cuda.synchronize()
+    t_tr = e0.elapsed_time(e1) / 200
+    res = {"infer_groups": infer_groups, "train_groups": train_groups, "infer_ms": round(t_inf, 4), "train_step_us": round(t_tr * 1e3, 1), "loss8": losses[-1]}
+    if ref_out is not None:
+        res["max_abs_diff_vs_ref"] = float(np.nanmax(np.abs(out0 - ref_out)))
+    nrc.Destroy()
+    return res, out0
+
+if __name__ == "__main__":
+    cfgs = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]] or [(0, 0), (0, 1), (0, 2), (2, 1), (3, 1)]
+    ref = None
+    for ig, tg in cfgs:
+        r, out = run(ig, tg, ref)
+        if ref is None: ref = out
+        print(json.dumps(r), flush=True)
