@@ -282,11 +282,13 @@ def run_ours(args):
     pin_tin = [torch.from_numpy(h_tin[i]).pin_memory() for i in range(2)]
     pin_tgt = [torch.from_numpy(h_tgt[i]).pin_memory() for i in range(2)]
 
+    np_in, np_out = [t.numpy() for t in pin_in], pin_out.numpy()
+    np_tin, np_tgt = [t.numpy() for t in pin_tin], [t.numpy() for t in pin_tgt]
+
     def e2e_step(i):
         s = i % 2
-        nrc.inference_host(pin_in[s].numpy(), True, out=pin_out.numpy())
-        for b in range(TRAIN_BATCHES):
-            nrc.training_step_host(pin_tin[s].numpy()[b * TRAIN_BATCH:(b + 1) * TRAIN_BATCH], pin_tgt[s].numpy()[b * TRAIN_BATCH:(b + 1) * TRAIN_BATCH])
+        # one InferAndTrain call on pinned host buffers: H2D of the records, kernels, D2H of the radiance + the loss
+        nrc.infer_and_train_host(np_in[s], np_out, np_tin[s], np_tgt[s], TRAIN_BATCH, True)
     for i in range(3):
         e2e_step(i)
     barrier()

@@ -106,6 +106,13 @@ int nrc_last_step_tensor(nrc_cache* c, int which, float* host_out);
 /* Host-buffer entry points (pageable or pinned host memory; H2D and D2H copies happen inside the call). */
 int nrc_inference_host(nrc_cache* c, const float* h_in, float* h_out, uint32_t n, int use_ema);
 int nrc_training_step_host(nrc_cache* c, const float* h_in, const float* h_target, uint32_t batch, float* loss_out);
+/* en::NeuralRadianceCache::InferAndTrain (src/NeuralRadianceCache.cu:97-156) on HOST buffers, one call per frame: inference
+ * of h_infer_in float[n_infer][5] -> h_infer_out float[n_infer][3] with the weights as they are on entry (EMA when use_ema),
+ * then n_batches training steps of `batch` records each from h_train_in float[n_batches*batch][5] / h_train_target
+ * float[...][3]; *loss_out = loss of the last batch (GetLoss).  H2D copies, kernels and D2H copies are pipelined over three
+ * streams and the host waits once at the end.  n_infer == 0 or n_batches == 0 skip the respective half. */
+int nrc_infer_and_train_host(nrc_cache* c, const float* h_infer_in, float* h_infer_out, uint32_t n_infer, const float* h_train_in,
+                             const float* h_train_target, uint32_t batch, uint32_t n_batches, int use_ema, float* loss_out);
 
 /* ------------------------------------------------------------------------------------------------
  * Scene + NrcHpmRenderer / McHpmRenderer

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnrchpm_b200.so")
+# NRCHPM_LIB selects an experimental build of the same library (scripts/build_variant.sh); development only
+LIB_PATH = os.environ.get("NRCHPM_LIB") or os.path.join(_HERE, "libnrchpm_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3
 
@@ -67,6 +68,7 @@ SIGNATURES = {
     "nrc_last_step_tensor": (_I, [_P, _I, _F]),
     "nrc_inference_host": (_I, [_P, _F, _F, _U32, _I]),
     "nrc_training_step_host": (_I, [_P, _F, _F, _U32, _F]),
+    "nrc_infer_and_train_host": (_I, [_P, _F, _F, _U32, _F, _F, _U32, _U32, _I, _F]),
     "hpm_scene_create": (_I, [C.POINTER(SceneDesc), _P, C.POINTER(_P)]),
     "hpm_scene_destroy": (_I, [_P]),
     "hpm_renderer_create": (_I, [_P, _P, C.POINTER(RenderConfig), _P, C.POINTER(_P)]),

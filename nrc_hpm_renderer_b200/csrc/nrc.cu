@@ -297,7 +297,7 @@ void NrcCache::get_params(int which, float* out) {
 void NrcCache::setup_kernels() {
     const int H = cfg_.n_hidden_layers;
     NRC_DISPATCH_INW(enc_.in_w, {
-        NRCHPM_CUDA(cudaFuncSetAttribute(nrc_forward_kernel<IN_W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem_bytes<IN_W>(H)));
+        NRCHPM_CUDA(cudaFuncSetAttribute(nrc_forward_kernel<IN_W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem_bytes<IN_W>(H, kInferWgs)));
         NRCHPM_CUDA(cudaFuncSetAttribute(nrc_forward_kernel<IN_W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem_bytes<IN_W>(H)));
         NRCHPM_CUDA(cudaFuncSetAttribute(nrc_backward_kernel<IN_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem_bytes<IN_W>(H)));
         NRCHPM_CUDA(cudaFuncSetAttribute(nrc_dw_kernel<IN_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDwSmemBytes));
@@ -332,9 +332,12 @@ void NrcCache::inference(const float* d_in, float* d_out, uint32_t n, bool use_e
         check_launch("nrc_forward2_kernel<infer>");
         return;
     }
-    launch_shape(tiles, grid, threads);
+    // persistent grid: kInferWgs warpgroups (tiles in flight) per CTA, kInferCtas CTAs per SM; small batches use fewer warpgroups
+    const uint32_t wgs = (uint32_t)std::max(1, std::min<int>(kInferWgs, (int)((tiles + sm_count_ * kInferCtas - 1) / (sm_count_ * kInferCtas))));
+    threads = wgs * 128;
+    grid = std::min<uint32_t>((tiles + wgs - 1) / wgs, (uint32_t)sm_count_ * kInferCtas);
     NRC_DISPATCH_INW(enc_.in_w, {
-        nrc_forward_kernel<IN_W, false><<<grid, threads, fwd_smem_bytes<IN_W>(cfg_.n_hidden_layers), s>>>(a);
+        nrc_forward_kernel<IN_W, false><<<grid, threads, fwd_smem_bytes<IN_W>(cfg_.n_hidden_layers, (int)wgs), s>>>(a);
     });
     check_launch("nrc_forward_kernel<infer>");
 }
@@ -574,6 +577,13 @@ int nrc_inference_host(nrc_cache* c, const float* h_in, float* h_out, uint32_t n
 int nrc_training_step_host(nrc_cache* c, const float* h_in, const float* h_tgt, uint32_t batch, float* loss_out) {
     return guard([&] { NRCHPM_REQUIRE(c && h_in && h_tgt, "null argument"); c->impl.training_step_host(h_in, h_tgt, batch, loss_out); });
 }
+int nrc_infer_and_train_host(nrc_cache* c, const float* h_in, float* h_out, uint32_t n, const float* h_tin, const float* h_tgt, uint32_t batch,
+                             uint32_t n_batches, int use_ema, float* loss_out) {
+    return guard([&] {
+        NRCHPM_REQUIRE(c && (n == 0 || (h_in && h_out)) && (n_batches == 0 || (h_tin && h_tgt)), "null argument");
+        c->impl.infer_and_train_host(h_in, h_out, n, h_tin, h_tgt, batch, n_batches, use_ema != 0, loss_out);
+    });
+}
 
 }  // extern "C"
 
@@ -593,25 +603,19 @@ void NrcCache::gradient_buffers(float** mlp, void** enc) {
 }
 // Host-buffer inference: the records are cut into chunks of whole persistent-grid rounds and pipelined over three streams
 // (H2D copy, compute, D2H copy), so PCIe transfers of chunk i+1 / i-1 overlap the kernel of chunk i.
-void NrcCache::inference_host(const float* h_in, float* h_out, uint32_t n, bool use_ema) {
-    if (n == 0) return;
-    host_in_.ensure((size_t)n * 5); host_out_.ensure((size_t)n * 3);
+void NrcCache::ensure_pipeline(uint32_t n_chunks) {
     if (!copy_in_stream_) {
         NRCHPM_CUDA(cudaStreamCreateWithFlags(&copy_in_stream_, cudaStreamNonBlocking));
         NRCHPM_CUDA(cudaStreamCreateWithFlags(&copy_out_stream_, cudaStreamNonBlocking));
         NRCHPM_CUDA(cudaStreamCreateWithFlags(&compute_stream_, cudaStreamNonBlocking));
     }
-    const uint32_t chunk = (uint32_t)sm_count_ * 2 * 2 * 4 * kTile;       // 4 tiles per resident warpgroup
-    const uint32_t n_chunks = (n + chunk - 1) / chunk;
-    while (pipe_events_.size() < 2 * (size_t)n_chunks + 1) {
+    while (pipe_events_.size() < 2 * (size_t)n_chunks + 3) {
         cudaEvent_t e; NRCHPM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         pipe_events_.push_back(e);
     }
-    // everything already queued on the cache's stream (e.g. a training step that changed the weights) comes first
-    cudaEvent_t ev_prev = pipe_events_[2 * (size_t)n_chunks];
-    NRCHPM_CUDA(cudaEventRecord(ev_prev, stream_));
-    NRCHPM_CUDA(cudaStreamWaitEvent(compute_stream_, ev_prev, 0));
-    NRCHPM_CUDA(cudaStreamWaitEvent(copy_in_stream_, ev_prev, 0));
+}
+// queues the chunked H2D -> kernel -> D2H pipeline; returns without waiting
+void NrcCache::queue_inference_pipeline(const float* h_in, float* h_out, uint32_t n, bool use_ema, uint32_t chunk, uint32_t n_chunks) {
     for (uint32_t c = 0; c < n_chunks; c++) {
         const uint32_t o = c * chunk, m = std::min(chunk, n - o);
         NRCHPM_CUDA(cudaMemcpyAsync(host_in_.ptr + (size_t)o * 5, h_in + (size_t)o * 5, (size_t)m * 5 * sizeof(float), cudaMemcpyHostToDevice, copy_in_stream_));
@@ -622,14 +626,64 @@ void NrcCache::inference_host(const float* h_in, float* h_out, uint32_t n, bool 
         NRCHPM_CUDA(cudaStreamWaitEvent(copy_out_stream_, pipe_events_[2 * c + 1], 0));
         NRCHPM_CUDA(cudaMemcpyAsync(h_out + (size_t)o * 3, host_out_.ptr + (size_t)o * 3, (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToHost, copy_out_stream_));
     }
+}
+void NrcCache::inference_host(const float* h_in, float* h_out, uint32_t n, bool use_ema) {
+    if (n == 0) return;
+    host_in_.ensure((size_t)n * 5); host_out_.ensure((size_t)n * 3);
+    const uint32_t chunk = (uint32_t)sm_count_ * 2 * 2 * 4 * kTile;       // 4 tiles per resident warpgroup
+    const uint32_t n_chunks = (n + chunk - 1) / chunk;
+    ensure_pipeline(n_chunks);
+    // everything already queued on the cache's stream (e.g. a training step that changed the weights) comes first
+    cudaEvent_t ev_prev = pipe_events_[2 * (size_t)n_chunks];
+    NRCHPM_CUDA(cudaEventRecord(ev_prev, stream_));
+    NRCHPM_CUDA(cudaStreamWaitEvent(compute_stream_, ev_prev, 0));
+    NRCHPM_CUDA(cudaStreamWaitEvent(copy_in_stream_, ev_prev, 0));
+    queue_inference_pipeline(h_in, h_out, n, use_ema, chunk, n_chunks);
     NRCHPM_CUDA(cudaStreamSynchronize(copy_out_stream_));
 }
 void NrcCache::training_step_host(const float* h_in, const float* h_tgt, uint32_t B, float* loss_out) {
-    host_in_.ensure((size_t)B * 5); host_tgt_.ensure((size_t)B * 3);
+    host_tin_.ensure((size_t)B * 5); host_tgt_.ensure((size_t)B * 3);
     cudaStream_t s = stream_;
-    NRCHPM_CUDA(cudaMemcpyAsync(host_in_.ptr, h_in, (size_t)B * 5 * sizeof(float), cudaMemcpyHostToDevice, s));
+    NRCHPM_CUDA(cudaMemcpyAsync(host_tin_.ptr, h_in, (size_t)B * 5 * sizeof(float), cudaMemcpyHostToDevice, s));
     NRCHPM_CUDA(cudaMemcpyAsync(host_tgt_.ptr, h_tgt, (size_t)B * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
-    training_step(host_in_.ptr, host_tgt_.ptr, B, true, s);
+    training_step(host_tin_.ptr, host_tgt_.ptr, B, true, s);
     if (loss_out) *loss_out = loss();
+}
+// en::NeuralRadianceCache::InferAndTrain (src/NeuralRadianceCache.cu:97-156) on HOST buffers in ONE call: the training records
+// travel first (they are small), the inference pipeline follows, the training steps are queued behind the last inference chunk
+// on the compute stream -- so they overlap the D2H copy of the last radiance chunks -- and the host waits once, at the end.
+// Inference reads the EMA weights of the previous frame, exactly like the reference's inference-then-train order.
+void NrcCache::infer_and_train_host(const float* h_in, float* h_out, uint32_t n, const float* h_tin, const float* h_tgt, uint32_t B,
+                                    uint32_t n_batches, bool use_ema, float* loss_out) {
+    const bool train = n_batches > 0 && B > 0;
+    if (train) NRCHPM_REQUIRE(B % kTile == 0, "training batch must be a positive multiple of 128");
+    if (n) { host_in_.ensure((size_t)n * 5); host_out_.ensure((size_t)n * 3); }
+    const size_t T = (size_t)B * n_batches;
+    if (train) { host_tin_.ensure(T * 5); host_tgt_.ensure(T * 3); ensure_train_scratch(B); }
+    const uint32_t chunk = (uint32_t)sm_count_ * 2 * 2 * 4 * kTile;
+    const uint32_t n_chunks = (n + chunk - 1) / chunk;
+    ensure_pipeline(n_chunks);
+    cudaEvent_t ev_prev = pipe_events_[2 * (size_t)n_chunks], ev_train = pipe_events_[2 * (size_t)n_chunks + 1], ev_done = pipe_events_[2 * (size_t)n_chunks + 2];
+    NRCHPM_CUDA(cudaEventRecord(ev_prev, stream_));
+    NRCHPM_CUDA(cudaStreamWaitEvent(compute_stream_, ev_prev, 0));
+    NRCHPM_CUDA(cudaStreamWaitEvent(copy_in_stream_, ev_prev, 0));
+    if (train) {
+        NRCHPM_CUDA(cudaMemcpyAsync(host_tin_.ptr, h_tin, T * 5 * sizeof(float), cudaMemcpyHostToDevice, copy_in_stream_));
+        NRCHPM_CUDA(cudaMemcpyAsync(host_tgt_.ptr, h_tgt, T * 3 * sizeof(float), cudaMemcpyHostToDevice, copy_in_stream_));
+        NRCHPM_CUDA(cudaEventRecord(ev_train, copy_in_stream_));
+    }
+    if (n) queue_inference_pipeline(h_in, h_out, n, use_ema, chunk, n_chunks);
+    if (train) {
+        NRCHPM_CUDA(cudaStreamWaitEvent(compute_stream_, ev_train, 0));
+        for (uint32_t b = 0; b < n_batches; b++)
+            training_step(host_tin_.ptr + (size_t)b * B * 5, host_tgt_.ptr + (size_t)b * B * 3, B, true, compute_stream_);
+        NRCHPM_CUDA(cudaMemcpyAsync(&loss_host_, loss_dev_.ptr, sizeof(float), cudaMemcpyDeviceToHost, compute_stream_));
+    }
+    // later work on the cache's own stream is ordered behind this call
+    NRCHPM_CUDA(cudaEventRecord(ev_done, compute_stream_));
+    NRCHPM_CUDA(cudaStreamWaitEvent(stream_, ev_done, 0));
+    NRCHPM_CUDA(cudaStreamSynchronize(compute_stream_));
+    NRCHPM_CUDA(cudaStreamSynchronize(copy_out_stream_));
+    if (train) { loss_valid_ = true; if (loss_out) *loss_out = loss_host_; }
 }
 }  // namespace nrchpm

@@ -53,6 +53,8 @@ public:
     void optimizer_step(cudaStream_t s);
     void inference_host(const float* h_in, float* h_out, uint32_t n, bool use_ema);
     void training_step_host(const float* h_in, const float* h_tgt, uint32_t B, float* loss_out);
+    void infer_and_train_host(const float* h_in, float* h_out, uint32_t n, const float* h_tin, const float* h_tgt, uint32_t B, uint32_t n_batches,
+                              bool use_ema, float* loss_out);
     void set_stream_for_loss(cudaStream_t s) { if (!initialised_) stream_ = s; }
 
     void get_params(int which, float* out);
@@ -70,6 +72,8 @@ private:
     void scatter_grid_field(int field, const float* d_src);
     void ensure_train_scratch(uint32_t B);
     void launch_shape(uint32_t tiles, uint32_t& grid, uint32_t& threads) const;
+    void ensure_pipeline(uint32_t n_chunks);
+    void queue_inference_pipeline(const float* h_in, float* h_out, uint32_t n, bool use_ema, uint32_t chunk, uint32_t n_chunks);
 
     NrcConfig cfg_;
     EncParams enc_;
@@ -80,7 +84,7 @@ private:
     DeviceBuffer<__half> w16_, ema16_, grad16_, x16_, acts_, dacts_, out16_, dout16_, dx16_;
     DeviceBuffer<uint32_t> steps_;
     DeviceBuffer<GridAdamState> grid_state_;       // Adam state of the encoding parameters, one 32-byte record per entry
-    DeviceBuffer<float> host_in_, host_out_, host_tgt_;
+    DeviceBuffer<float> host_in_, host_out_, host_tin_, host_tgt_;
     uint32_t scratch_batch_ = 0, last_batch_ = 0, dw_chunks_ = 0, current_step_ = 0;
     const float* dw_source_ = nullptr;
     bool grid_grad_dirty_ = false, grads_pending_ = false, keep_dx_ = true, loss_valid_ = true, initialised_ = false;

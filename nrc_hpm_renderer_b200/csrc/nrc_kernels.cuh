@@ -81,11 +81,21 @@ __device__ __forceinline__ void encode_position(const EncParams& e, const __half
             //  * the two corners of an x-edge sit in ONE aligned 8-byte word whenever their indices differ only in bit 0
             //    (dense levels: x even; coherent-prime hash, whose x prime is 1: x even) -> one 64-bit load instead of
             //    two 32-bit loads, i.e. one L1 wavefront instead of two for half of all edges.
+            //  * tcnn's stride arithmetic wraps in uint32 for resolutions >= 2^16 (common_device.h:842-868): the z stride (and at
+            //    the finest level the y stride too) is 0 modulo the table size, so corners k and k+4 (k and k+2) are the SAME
+            //    entry.  That is a per-level constant, hence a warp-uniform branch: the aliasing corners reuse the loaded value.
+            const uint32_t hs_m = e.level_hsize[l] - 1u;
+            const bool lin = e.level_hash[l] == 0 && (e.level_hsize[l] & hs_m) == 0;
+            const bool dupz = lin && (e.level_s2[l] & hs_m) == 0;
+            const bool dupy = dupz && (e.level_s1[l] & hs_m) == 0;
             __half2 v[8];
 #pragma unroll
             for (int k = 0; k < 8; k += 2) {
+                if ((k >= 4 && dupz) || (k == 2 && dupy)) { v[k] = v[k & (k >= 4 ? 3 : 1)]; v[k + 1] = v[(k + 1) & (k >= 4 ? 3 : 1)]; continue; }
                 const uint32_t i0 = c.idx[k], i1 = c.idx[k + 1];
-                const bool n0 = c.w[k] != 0.0f, n1 = c.w[k + 1] != 0.0f;
+                bool n0 = c.w[k] != 0.0f, n1 = c.w[k + 1] != 0.0f;
+                if (k < 4 && dupz) { n0 |= c.w[k + 4] != 0.0f; n1 |= c.w[k + 5] != 0.0f; }
+                if (k == 0 && dupy) { n0 |= (c.w[2] != 0.0f) | (c.w[6] != 0.0f); n1 |= (c.w[3] != 0.0f) | (c.w[7] != 0.0f); }
                 const bool paired = (i0 ^ i1) == 1u;
                 // predicated, branch-free: one 64-bit load of the aligned word holding corner 0 (and corner 1 when paired),
                 // plus a 32-bit load of corner 1 only when it lives elsewhere
@@ -180,10 +190,10 @@ __device__ __forceinline__ void encode_direction_pad(const EncParams& e, float t
     }
 }
 
-template <class Put>
+template <int UNROLL = 2, class Put>
 __device__ __forceinline__ void encode_record(const EncParams& e, const __half2* __restrict__ grid, float x0, float x1, float x2,
                                               float th, float ph, Put& put) {
-    encode_position(e, grid, x0, x1, x2, 0, e.n_levels, put);
+    encode_position<UNROLL>(e, grid, x0, x1, x2, 0, e.n_levels, put);
     encode_direction_pad(e, th, ph, put);
 }
 
@@ -274,18 +284,37 @@ struct FwdArgs {
 
 constexpr uint32_t kColD = 0, kColA = 96, kColsPerWg = 128;
 
+// Shape of the inference instantiation (compile-time experiment knobs; defaults = measured best): warpgroups per CTA, CTAs per
+// SM, hash-grid levels whose gathers are issued back to back.  More than 4 warpgroups per CTA pack their TMEM columns
+// (64 accumulator + 32 operand columns each) at a stride of 96 instead of 128.
+#ifndef NRC_INFER_WGS
+#define NRC_INFER_WGS 2
+#endif
+#ifndef NRC_INFER_CTAS
+#define NRC_INFER_CTAS 2
+#endif
+#ifndef NRC_INFER_UNROLL
+#define NRC_INFER_UNROLL 2
+#endif
+constexpr int kInferWgs = NRC_INFER_WGS, kInferCtas = NRC_INFER_CTAS;
+__host__ __device__ constexpr uint32_t fwd_wg_stride(int wgs) { return wgs * 128 <= 512 ? 128u : 96u; }
+__host__ __device__ constexpr uint32_t fwd_tmem_cols(int wgs) { return wgs * fwd_wg_stride(wgs) <= 128 ? 128u : wgs * fwd_wg_stride(wgs) <= 256 ? 256u : 512u; }
+static_assert(kInferWgs >= 1 && kInferWgs <= 5 && kInferCtas * fwd_tmem_cols(kInferWgs) <= 512, "TMEM budget");
+
 template <int IN_W>
-__host__ __device__ constexpr size_t fwd_smem_bytes(int n_hidden) {
-    return (size_t)IN_W * 128 + (size_t)(n_hidden - 1) * 8192 + 2048 + 2 * (size_t)IN_W * 256;
+__host__ __device__ constexpr size_t fwd_smem_bytes(int n_hidden, int wgs = 2) {
+    return (size_t)IN_W * 128 + (size_t)(n_hidden - 1) * 8192 + 2048 + (size_t)wgs * IN_W * 256;
 }
 
 template <int IN_W, bool TRAIN>
-__global__ void __launch_bounds__(kFwdThreads, 2) nrc_forward_kernel(const __grid_constant__ FwdArgs a) {
+__global__ void __launch_bounds__(TRAIN ? kFwdThreads : kInferWgs * 128, TRAIN ? 2 : kInferCtas) nrc_forward_kernel(const __grid_constant__ FwdArgs a) {
     using namespace tc05;
+    constexpr int kMaxWg = TRAIN ? 2 : kInferWgs;
+    constexpr uint32_t kStride = fwd_wg_stride(kMaxWg), kColAq = kStride - 32, kAlloc = fwd_tmem_cols(kMaxWg);
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t mbar[2];
+    __shared__ uint64_t mbar[kMaxWg];
     __shared__ uint32_t tmem_base_s;
-    __shared__ float loss_red[2][4];
+    __shared__ float loss_red[kMaxWg][4];
     const int tid = threadIdx.x, wg = tid >> 7, r = tid & 127, warp = tid >> 5, lane = tid & 31;
     const int nthreads = blockDim.x, nwg = nthreads >> 7;      // 2 warpgroups per CTA for large batches, 1 for small ones
     const int H = a.n_hidden;
@@ -294,8 +323,8 @@ __global__ void __launch_bounds__(kFwdThreads, 2) nrc_forward_kernel(const __gri
     uint8_t* wo_s = wh_s + (H - 1) * 8192;
     uint8_t* x_s = wo_s + 2048 + wg * (IN_W * 256);
 
-    if (warp == 0) { tmem_alloc(&tmem_base_s, 2 * kColsPerWg); tmem_relinquish(); }
-    if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); fence_mbar_init(); }
+    if (warp == 0) { tmem_alloc(&tmem_base_s, kAlloc); tmem_relinquish(); }
+    if (tid == 0) { for (int g = 0; g < kMaxWg; g++) mbar_init(&mbar[g], 1); fence_mbar_init(); }
     copy_weights_kmajor(w0_s, a.params, kWidth, IN_W, tid, nthreads);
     for (int l = 1; l < H; l++) copy_weights_kmajor(wh_s + (l - 1) * 8192, a.params + IN_W * kWidth + (l - 1) * kWidth * kWidth, kWidth, kWidth, tid, nthreads);
     copy_weights_kmajor(wo_s, a.params + IN_W * kWidth + (H - 1) * kWidth * kWidth, kOutPad, kWidth, tid, nthreads);
@@ -304,7 +333,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) nrc_forward_kernel(const __gri
     __syncthreads();
     fence_after();
 
-    const uint32_t tD = tmem_base_s + wg * kColsPerWg + kColD, tA = tmem_base_s + wg * kColsPerWg + kColA;
+    const uint32_t tD = tmem_base_s + wg * kStride + kColD, tA = tmem_base_s + wg * kStride + kColAq;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t idesc64 = make_idesc_f16(128, 64), idesc16 = make_idesc_f16(128, 16);
     const uint32_t x_addr = smem_u32(x_s), w0_addr = smem_u32(w0_s), wh_addr = smem_u32(wh_s), wo_addr = smem_u32(wo_s);
@@ -328,7 +357,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) nrc_forward_kernel(const __gri
         }
         uint8_t* my_row = x_s + (r >> 3) * (IN_W * 16) + (r & 7) * 16;
         SmemRowPut put{my_row};
-        encode_record(a.enc, grid, x0, x1, x2, th, ph, put);
+        encode_record<TRAIN ? 2 : NRC_INFER_UNROLL>(a.enc, grid, x0, x1, x2, th, ph, put);
         fence_proxy_async_smem();
         fence_before();
         named_bar_sync(1 + wg, 128);
@@ -442,7 +471,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) nrc_forward_kernel(const __gri
     }
     fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base_s, 2 * kColsPerWg);
+    if (warp == 0) tmem_dealloc(tmem_base_s, kAlloc);
 }
 
 // ---------------------------------------------------------------------------------------------- backward

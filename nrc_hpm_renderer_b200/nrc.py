@@ -145,3 +145,13 @@ class NeuralRadianceCache:
         v = C.c_float()
         _lib.check(_lib.lib().nrc_training_step_host(self._h, _fp(rec), _fp(target), len(rec), C.byref(v)))
         return float(v.value)
+
+    def infer_and_train_host(self, rec: np.ndarray, out: np.ndarray, train_rec: np.ndarray | None, train_target: np.ndarray | None,
+                             batch: int = 0, use_ema=True) -> float:
+        """``InferAndTrain`` on host buffers in one call (pipelined copies, one host wait); returns the last batch's loss"""
+        n = 0 if rec is None else len(rec)
+        nb = 0 if train_rec is None or batch == 0 else len(train_rec) // batch
+        v = C.c_float()
+        _lib.check(_lib.lib().nrc_infer_and_train_host(self._h, _fp(rec) if n else None, _fp(out) if n else None, n,
+                                                       _fp(train_rec) if nb else None, _fp(train_target) if nb else None, batch, nb, int(use_ema), C.byref(v)))
+        return float(v.value)

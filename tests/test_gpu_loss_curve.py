@@ -1,0 +1,58 @@
+"""BASELINE north_star: "matching loss curves over 1000 steps".  The CUDA path trains for 1000 steps on the same records, in the
+same order, with the same initial weights (bit-exact, tests/test_gpu_nrc.py) as the reference's own tiny-cuda-nn did when the
+fixture tests/golden/tcnn_loss1000_*.npz was recorded on a B200 (generator: tests/golden/make_tcnn_loss_curve.py).
+Tolerance: mean |loss - loss_ref| / loss_ref over every 50-step window <= 5 %; the two trajectories see different
+rounding (fp32 vs fp16 accumulation, atomic order) so single steps are compared only through the windows.  After the last step
+the two caches must predict the held-out records alike."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _generator():
+    spec = importlib.util.spec_from_file_location("make_tcnn_loss_curve", os.path.join(ROOT, "tests", "golden", "make_tcnn_loss_curve.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    return m
+
+
+@pytest.mark.parametrize("name", ["hash_ob_d6", "tri_ob_d5"])
+def test_loss_curve_1000_steps_vs_tcnn(name):
+    import torch
+    from nrc_hpm_renderer_b200 import AppConfig
+    from nrc_hpm_renderer_b200.nrc import NeuralRadianceCache
+    path = os.path.join(ROOT, "tests", "golden", f"tcnn_loss1000_{name}.npz")
+    if not os.path.exists(path):
+        pytest.skip("fixture not recorded yet")
+    z = np.load(path)
+    B, steps = int(z["batch"]), int(z["steps"])
+    tin, tgt, held = _generator().training_data(int(z["seed"]), B, steps)
+    assert np.array_equal(held, z["held_out"])                     # same generator, same records
+    app = AppConfig.default()
+    app.pos_enc_id, app.dir_enc_id, app.nn_depth, app.learning_rate = int(z["pos"]), int(z["dir"]), int(z["depth"]), float(z["lr"])
+    c = NeuralRadianceCache(app)
+    d_in, d_tgt = torch.from_numpy(tin).cuda(), torch.from_numpy(tgt).cuda()
+    losses = np.empty(steps, np.float32)
+    for s in range(steps):
+        c.training_step(d_in[s * B:(s + 1) * B], d_tgt[s * B:(s + 1) * B], B, True)
+        losses[s] = c.GetLoss()
+    ref = z["losses"]
+    assert np.all(np.isfinite(losses))
+    assert abs(losses[0] - ref[0]) <= 1e-3 * ref[0]                 # identical weights and records: the first loss is the same number
+    w = 50
+    worst = max(abs(losses[i:i + w].mean() - ref[i:i + w].mean()) / ref[i:i + w].mean() for i in range(0, steps, w))
+    assert worst <= 0.05, worst
+    assert ref[-w:].mean() < 0.25 * ref[:w].mean() and losses[-w:].mean() < 0.25 * losses[:w].mean()      # both actually learned
+    out = torch.zeros((len(held), 3), dtype=torch.float32, device="cuda")
+    c.inference(torch.from_numpy(held).cuda(), out, len(held), use_ema=True)
+    torch.cuda.synchronize()
+    ours, theirs, truth = out.cpu().numpy(), z["infer_ema_final"], z["held_out_target"]
+    e_ours = np.linalg.norm(ours - truth) / np.linalg.norm(truth)
+    e_theirs = np.linalg.norm(theirs - truth) / np.linalg.norm(truth)
+    assert e_ours <= 1.15 * e_theirs + 0.01, (e_ours, e_theirs)   # as good a fit as the reference's
+    assert np.linalg.norm(ours - theirs) / np.linalg.norm(theirs) <= 2.0 * max(e_ours, e_theirs) + 0.01

@@ -220,3 +220,29 @@ def test_host_entry_points_and_errors():
         c.training_step_host(rec[:100], rng.random((100, 3), dtype=np.float32))      # not a multiple of 128
     with pytest.raises(_lib.NrcHpmError):
         N.NeuralRadianceCache(config_json={"encoding": {"otype": "SphericalHarmonics"}})
+
+
+def test_infer_and_train_host_equals_separate_calls():
+    """nrc_infer_and_train_host (one pipelined call per frame) == nrc_inference_host followed by nrc_training_step_host per batch:
+    identical radiance (inference is deterministic and reads the pre-training EMA weights) and the same loss trajectory (the
+    forward pass and the loss are deterministic; the fp16 atomics of the grid gradient make later losses agree to tolerance)."""
+    from nrc_hpm_renderer_b200 import AppConfig, nrc as N
+    rng = np.random.default_rng(5)
+    n, B, nb = 700_000, 1024, 3                       # > 2 pipeline chunks, ragged last chunk
+    rec = rng.random((n, 5), dtype=np.float32)
+    tin = rng.random((B * nb, 5), dtype=np.float32)
+    tgt = (rng.random((B * nb, 3), dtype=np.float32) * 2).astype(np.float32)
+    a, b = N.NeuralRadianceCache(AppConfig.default()), N.NeuralRadianceCache(AppConfig.default())
+    out_a, out_b = np.full((n, 3), -1, np.float32), None
+    for frame in range(3):
+        la = a.infer_and_train_host(rec, out_a, tin, tgt, B, True)
+        out_b = b.inference_host(rec, use_ema=True)
+        for k in range(nb):
+            lb = b.training_step_host(tin[k * B:(k + 1) * B], tgt[k * B:(k + 1) * B])
+        assert np.array_equal(out_a, out_b) if frame == 0 else rel_err(out_a, out_b) <= 1e-2
+        assert abs(la - lb) <= 2e-3 * abs(lb)
+        assert a.GetLoss() == la
+    assert np.any(out_a != 0)                        # the EMA weights moved after the first frame
+    # halves can be skipped
+    assert np.isfinite(a.infer_and_train_host(None, None, tin, tgt, B, True))
+    a.infer_and_train_host(rec[:4096], out_a[:4096], None, None, 0, True)
