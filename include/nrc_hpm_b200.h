@@ -199,6 +199,19 @@ int hpm_buffer_info(hpm_renderer* r, int which, void** d_ptr, size_t* bytes);
 int hpm_read_buffer(hpm_renderer* r, int which, void* host_out, size_t bytes);
 int hpm_write_buffer(hpm_renderer* r, int which, const void* host_in, size_t bytes);
 
+/* Reference::Result (include/engine/graphics/Reference.hpp:17-29) -- what Reference::CompareNrc / CompareMc
+ * (src/Reference.cpp:72-171; data/shader/ref/cmp1.comp, norm.comp, cmp2.comp) compute for a frame against a reference
+ * frame, over the pixels whose reference alpha is not 0: mse = mean |cmp.rgb - ref.rgb|^2 / 3, the two image means,
+ * own_var = mean |cmp.rgb - own_mean|^2 / 3.  Derived: bias = own_mean - ref_mean, rBias = bias / ref_mean,
+ * rVar = own_var / ref_mean, CV = sqrt(own_var) / own_mean (Reference.cpp:10-28). */
+typedef struct hpm_compare_result {
+    float mse, ref_mean, own_mean, own_var;
+    uint32_t valid_pixel_count;
+} hpm_compare_result;
+/* both images: device float[W*H][4] (HPM_BUF_OUTPUT layout).  Deterministic (fixed summation order). */
+int hpm_compare_images(const float* d_ref_rgba, const float* d_cmp_rgba, uint32_t width, uint32_t height,
+                       hpm_compare_result* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,8 @@ Host-side mirror of the reference interface (same names and argument meaning):
     Camera                           reference src/Camera.cpp (matrix math only)
     NeuralRadianceCache              reference include/engine/graphics/NeuralRadianceCache.hpp
     HpmScene, NrcHpmRenderer, McHpmRenderer
+    Reference, Result                reference include/engine/graphics/Reference.hpp, src/Reference.cpp (frame metrics)
+    exr.read_exr / exr.write_exr     the reference's on-disk frame format (tinyexr SaveEXR / LoadEXR)
 The compute lives in libnrchpm_b200.so (C ABI: include/nrc_hpm_b200.h); there is no CPU fallback.
 """
 from .config import AppConfig, HpmSceneConfig, calc_train_subset, encoding_json, sky_size  # noqa: F401
@@ -20,4 +22,7 @@ def __getattr__(name):
     if name in ("HpmScene", "NrcHpmRenderer", "McHpmRenderer", "make_render_config"):
         from . import renderer
         return getattr(renderer, name)
+    if name in ("Reference", "Result"):
+        from . import reference
+        return getattr(reference, name)
     raise AttributeError(name)

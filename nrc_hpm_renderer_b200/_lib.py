@@ -36,6 +36,10 @@ class RenderConfig(C.Structure):
                 ("show_nrc", C.c_uint32), ("compact_inference", C.c_uint32), ("x_begin", C.c_uint32), ("x_end", C.c_uint32)]
 
 
+class CompareResult(C.Structure):
+    _fields_ = [("mse", C.c_float), ("ref_mean", C.c_float), ("own_mean", C.c_float), ("own_var", C.c_float), ("valid_pixel_count", C.c_uint32)]
+
+
 # name -> (restype, argtypes); every exported symbol of include/nrc_hpm_b200.h is listed here (tests check it)
 _P, _F, _U32, _U64, _SZ, _I = C.c_void_p, C.POINTER(C.c_float), C.c_uint32, C.c_uint64, C.c_size_t, C.c_int
 SIGNATURES = {
@@ -85,6 +89,7 @@ SIGNATURES = {
     "hpm_buffer_info": (_I, [_P, _I, C.POINTER(_P), C.POINTER(_SZ)]),
     "hpm_read_buffer": (_I, [_P, _I, _P, _SZ]),
     "hpm_write_buffer": (_I, [_P, _I, _P, _SZ]),
+    "hpm_compare_images": (_I, [_P, _P, _U32, _U32, C.POINTER(CompareResult), _P]),
 }
 
 _lib = None

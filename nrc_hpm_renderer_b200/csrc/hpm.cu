@@ -264,4 +264,29 @@ int hpm_buffer_info(hpm_renderer* r, int which, void** p, size_t* b) { return gu
 int hpm_read_buffer(hpm_renderer* r, int which, void* host, size_t bytes) { return guard([&] { NRCHPM_REQUIRE(r && host, "null argument"); r->impl.read_buffer(which, host, bytes); }); }
 int hpm_write_buffer(hpm_renderer* r, int which, const void* host, size_t bytes) { return guard([&] { NRCHPM_REQUIRE(r && host, "null argument"); r->impl.write_buffer(which, host, bytes); }); }
 
+
+// Reference::CompareNrc / CompareMc (src/Reference.cpp:72-171): image statistics on the device, one host read-back of 20 bytes
+int hpm_compare_images(const float* d_ref_rgba, const float* d_cmp_rgba, uint32_t width, uint32_t height, hpm_compare_result* out, void* stream) {
+    return guard([&] {
+        NRCHPM_REQUIRE(d_ref_rgba && d_cmp_rgba && out && width && height, "null argument");
+        cudaStream_t s = (cudaStream_t)stream;
+        const size_t n = (size_t)width * height;
+        const int blocks = (int)std::min<size_t>(kCmpBlocks, (n + kCmpThreads - 1) / kCmpThreads);
+        DeviceBuffer<double> partials; partials.allocate((size_t)blocks * 5);
+        DeviceBuffer<float> result; result.allocate(5);
+        const float4* ref = reinterpret_cast<const float4*>(d_ref_rgba); const float4* cmp = reinterpret_cast<const float4*>(d_cmp_rgba);
+        hpm_compare_pass1_kernel<<<blocks, kCmpThreads, 0, s>>>(ref, cmp, n, partials.ptr);
+        check_launch("hpm_compare_pass1_kernel");
+        hpm_compare_pass2_kernel<<<blocks, kCmpThreads, 0, s>>>(ref, cmp, n, partials.ptr, blocks, partials.ptr + 4 * (size_t)blocks);
+        check_launch("hpm_compare_pass2_kernel");
+        hpm_compare_finish_kernel<<<1, 1, 0, s>>>(partials.ptr, partials.ptr + 4 * (size_t)blocks, blocks, result.ptr);
+        check_launch("hpm_compare_finish_kernel");
+        float h[5];
+        NRCHPM_CUDA(cudaMemcpyAsync(h, result.ptr, sizeof(h), cudaMemcpyDeviceToHost, s));
+        NRCHPM_CUDA(cudaStreamSynchronize(s));
+        out->mse = h[0]; out->ref_mean = h[1]; out->own_mean = h[2]; out->own_var = h[3];
+        std::memcpy(&out->valid_pixel_count, &h[4], 4);
+    });
+}
+
 }  // extern "C"

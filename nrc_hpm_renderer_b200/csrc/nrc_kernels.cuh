@@ -20,6 +20,11 @@
 #include "tc05.cuh"
 #include "nrc_types.h"
 
+// width of the hash-grid gather loads: 64 (aligned pair of entries) or 128 (aligned group of four entries)
+#ifndef NRC_GATHER_BITS
+#define NRC_GATHER_BITS 64
+#endif
+
 namespace nrchpm {
 
 // ---------------------------------------------------------------------------------------------- encodings
@@ -96,6 +101,18 @@ __device__ __forceinline__ void encode_position(const EncParams& e, const __half
                 bool n0 = c.w[k] != 0.0f, n1 = c.w[k + 1] != 0.0f;
                 if (k < 4 && dupz) { n0 |= c.w[k + 4] != 0.0f; n1 |= c.w[k + 5] != 0.0f; }
                 if (k == 0 && dupy) { n0 |= (c.w[2] != 0.0f) | (c.w[6] != 0.0f); n1 |= (c.w[3] != 0.0f) | (c.w[7] != 0.0f); }
+#if NRC_GATHER_BITS == 128
+                // 128-bit flavour: the aligned group of four entries holds both corners for three of four x positions
+                // (x mod 4 != 3), so only a quarter of the edges need the second load -- 1.25 L1 wavefronts per edge, not 1.5
+                const bool paired = (i0 ^ i1) < 4u;
+                uint4 q = make_uint4(0u, 0u, 0u, 0u);
+                if (n0 | (paired & n1)) q = *reinterpret_cast<const uint4*>(base + (i0 & ~3u));
+                uint32_t a1 = 0u;
+                if (!paired & n1) a1 = *reinterpret_cast<const uint32_t*>(base + i1);
+                const uint32_t a0 = (i0 & 2u) ? ((i0 & 1u) ? q.w : q.z) : ((i0 & 1u) ? q.y : q.x);
+                const uint32_t a1q = (i1 & 2u) ? ((i1 & 1u) ? q.w : q.z) : ((i1 & 1u) ? q.y : q.x);
+                a1 = paired ? a1q : a1;
+#else
                 const bool paired = (i0 ^ i1) == 1u;
                 // predicated, branch-free: one 64-bit load of the aligned word holding corner 0 (and corner 1 when paired),
                 // plus a 32-bit load of corner 1 only when it lives elsewhere
@@ -105,6 +122,7 @@ __device__ __forceinline__ void encode_position(const EncParams& e, const __half
                 if (!paired & n1) a1 = *reinterpret_cast<const uint32_t*>(base + i1);
                 const uint32_t a0 = (i0 & 1u) ? q.y : q.x;
                 a1 = paired ? ((i1 & 1u) ? q.y : q.x) : a1;
+#endif
                 v[k] = *reinterpret_cast<const __half2*>(&a0);
                 v[k + 1] = *reinterpret_cast<const __half2*>(&a1);
             }

@@ -136,6 +136,11 @@ class NrcHpmRenderer:
         """outputImage as float32 [H][W][4]"""
         return self.read(BUF_OUTPUT).reshape(self.height, self.width, 4)
 
+    def ExportOutputImageToFile(self, file_path: str):
+        """outputImage -> RGBA32F OpenEXR, the file tinyexr's SaveEXR writes (reference src/NrcHpmRenderer.cu:437-493)"""
+        from . import exr
+        exr.write_exr(file_path, self.GetImage())
+
     def Destroy(self):
         if self._h:
             _lib.check(_lib.lib().hpm_renderer_destroy(self._h))

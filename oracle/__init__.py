@@ -184,6 +184,20 @@ def mc_render(scene, cfg, cam, frame_random, path_length, blend_factor, output):
 
 
 # ------------------------------------------------------------------ NRC
+def compare_images(ref_rgba: np.ndarray, cmp_rgba: np.ndarray) -> dict:
+    """Reference::Result restated in numpy (float64 sums): data/shader/ref/cmp1.comp:25-41 (mse, refMean, ownMean, count over the
+    pixels with ref alpha != 0), norm.comp:19-24 (divide by the count), cmp2.comp:25-40 (ownVar around the scalar ownMean)."""
+    ref, cmp_ = np.asarray(ref_rgba, np.float32).reshape(-1, 4), np.asarray(cmp_rgba, np.float32).reshape(-1, 4)
+    valid = ref[:, 3] != 0.0
+    n = int(valid.sum())
+    r, c = ref[valid, :3].astype(np.float64), cmp_[valid, :3].astype(np.float64)
+    if n == 0:
+        return {"mse": 0.0, "refMean": 0.0, "ownMean": 0.0, "ownVar": 0.0, "validPixelCount": 0}
+    own_mean = float((c.sum(1) / 3).sum() / n)
+    return {"mse": float((((c - r) ** 2).sum(1) / 3).sum() / n), "refMean": float((r.sum(1) / 3).sum() / n), "ownMean": own_mean,
+            "ownVar": float((((c - np.float64(np.float32(own_mean))) ** 2).sum(1) / 3).sum() / n), "validPixelCount": n}
+
+
 def nrc_config(pos_enc=0, dir_enc=0, n_hidden_layers=6, n_neurons=64, oneblob_soa_bug=1, accum_fp16=0, learning_rate=0.01,
                ema_decay=0.99) -> NrcoConfig:
     return NrcoConfig(pos_enc, dir_enc, n_neurons, n_hidden_layers, oneblob_soa_bug, accum_fp16, 16, 19, 16, 2.0, 12, 4, 4,
