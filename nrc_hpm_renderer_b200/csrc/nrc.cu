@@ -110,6 +110,7 @@ void NrcCache::derive() {
     n_grid_ = 0;
     if (c.pos_enc == POS_HASHGRID) {                                    // grid.h:699-724
         uint32_t offset = 0;
+        e.all_pow2 = 1;
         const float log2_pls = std::log2(c.per_level_scale);
         for (int i = 0; i < c.n_levels; i++) {
             const float scale = grid_scale(i, log2_pls, c.base_resolution);
@@ -120,6 +121,7 @@ void NrcCache::derive() {
             p = std::min(p, 1u << c.log2_hashmap_size);
             e.level_scale[i] = scale;
             e.level_hsize[i] = p;
+            if (p & (p - 1)) e.all_pow2 = 0;
             e.level_offset[i] = offset;
             // grid_index (common_device.h:668-690) with its uint32 stride arithmetic, including the wrap-around for res >= 2^16
             uint32_t stride = 1, s[3] = {0, 0, 0};
@@ -219,7 +221,7 @@ NrcCache::NrcCache(const NrcConfig& cfg, uint64_t seed) : cfg_(cfg) {
 
 NrcCache::~NrcCache() {
     for (auto e : pipe_events_) cudaEventDestroy(e);
-    if (copy_in_stream_) { cudaStreamDestroy(copy_in_stream_); cudaStreamDestroy(copy_out_stream_); cudaStreamDestroy(compute_stream_); }
+    if (copy_in_stream_) { cudaStreamDestroy(copy_in_stream_); cudaStreamDestroy(copy_out_stream_); cudaStreamDestroy(compute_stream_); cudaStreamDestroy(train_stream_); }
 }
 
 void NrcCache::scatter_grid_field(int field, const float* d_src) {
@@ -297,7 +299,7 @@ void NrcCache::get_params(int which, float* out) {
 void NrcCache::setup_kernels() {
     const int H = cfg_.n_hidden_layers;
     NRC_DISPATCH_INW(enc_.in_w, {
-        NRCHPM_CUDA(cudaFuncSetAttribute(nrc_forward_kernel<IN_W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem_bytes<IN_W>(H, kInferWgs)));
+        NRCHPM_CUDA(cudaFuncSetAttribute(nrc_forward_kernel<IN_W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fwd_smem_bytes<IN_W>(H, kInferWgs) + infer_smem_level_bytes())));
         NRCHPM_CUDA(cudaFuncSetAttribute(nrc_forward_kernel<IN_W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem_bytes<IN_W>(H)));
         NRCHPM_CUDA(cudaFuncSetAttribute(nrc_backward_kernel<IN_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem_bytes<IN_W>(H)));
         NRCHPM_CUDA(cudaFuncSetAttribute(nrc_dw_kernel<IN_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDwSmemBytes));
@@ -310,6 +312,13 @@ void NrcCache::setup_kernels() {
     if (const char* v = std::getenv("NRCHPM_TRAIN_GROUPS")) train_groups_ = std::max(0, std::min(1, std::atoi(v)));
 }
 
+// bytes of the coarse hash-grid levels the inference kernel stages in shared memory (0: none)
+size_t NrcCache::infer_smem_level_bytes() const {
+    if (NRC_SMEM_LEVELS <= 0 || enc_.pos_enc != POS_HASHGRID || enc_.n_levels <= NRC_SMEM_LEVELS) return 0;
+    const size_t bytes = (size_t)enc_.level_offset[NRC_SMEM_LEVELS] * 4;
+    return (bytes % 16 == 0 && bytes <= 32768) ? bytes : 0;
+}
+
 void NrcCache::encode(const float* d_in, uint32_t n, bool use_ema, void* d_out_half, cudaStream_t s) {
     if (n == 0) return;
     nrc_encode_kernel<<<(n + 127) / 128, 128, 0, s>>>(enc_, use_ema ? ema16_.ptr : w16_.ptr, (uint32_t)n_mlp_, d_in, n, (__half*)d_out_half);
@@ -319,7 +328,7 @@ void NrcCache::encode(const float* d_in, uint32_t n, bool use_ema, void* d_out_h
 void NrcCache::inference(const float* d_in, float* d_out, uint32_t n, bool use_ema, const uint32_t* d_indices, const uint32_t* d_count, cudaStream_t s) {
     if (n == 0) return;
     FwdArgs a{};
-    a.enc = enc_; a.params = use_ema ? ema16_.ptr : w16_.ptr; a.n_mlp = (uint32_t)n_mlp_; a.n_hidden = cfg_.n_hidden_layers;
+    a.enc = enc_; a.params = infer_params_override_ ? infer_params_override_ : use_ema ? ema16_.ptr : w16_.ptr; a.n_mlp = (uint32_t)n_mlp_; a.n_hidden = cfg_.n_hidden_layers;
     a.in = d_in; a.indices = d_indices; a.d_count = d_count; a.n = n; a.out = d_out;
     const uint32_t tiles = (n + kTile - 1) / kTile;
     uint32_t grid, threads;
@@ -336,8 +345,10 @@ void NrcCache::inference(const float* d_in, float* d_out, uint32_t n, bool use_e
     const uint32_t wgs = (uint32_t)std::max(1, std::min<int>(kInferWgs, (int)((tiles + sm_count_ * kInferCtas - 1) / (sm_count_ * kInferCtas))));
     threads = wgs * 128;
     grid = std::min<uint32_t>((tiles + wgs - 1) / wgs, (uint32_t)sm_count_ * kInferCtas);
+    const size_t lvl_bytes = infer_smem_level_bytes();
+    if (lvl_bytes) { a.smem_levels = NRC_SMEM_LEVELS; a.smem_level_entries = (uint32_t)(lvl_bytes / 4); }
     NRC_DISPATCH_INW(enc_.in_w, {
-        nrc_forward_kernel<IN_W, false><<<grid, threads, fwd_smem_bytes<IN_W>(cfg_.n_hidden_layers, (int)wgs), s>>>(a);
+        nrc_forward_kernel<IN_W, false><<<grid, threads, fwd_smem_bytes<IN_W>(cfg_.n_hidden_layers, (int)wgs) + lvl_bytes, s>>>(a);
     });
     check_launch("nrc_forward_kernel<infer>");
 }
@@ -608,8 +619,9 @@ void NrcCache::ensure_pipeline(uint32_t n_chunks) {
         NRCHPM_CUDA(cudaStreamCreateWithFlags(&copy_in_stream_, cudaStreamNonBlocking));
         NRCHPM_CUDA(cudaStreamCreateWithFlags(&copy_out_stream_, cudaStreamNonBlocking));
         NRCHPM_CUDA(cudaStreamCreateWithFlags(&compute_stream_, cudaStreamNonBlocking));
+        NRCHPM_CUDA(cudaStreamCreateWithFlags(&train_stream_, cudaStreamNonBlocking));
     }
-    while (pipe_events_.size() < 2 * (size_t)n_chunks + 3) {
+    while (pipe_events_.size() < 2 * (size_t)n_chunks + 5) {
         cudaEvent_t e; NRCHPM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         pipe_events_.push_back(e);
     }
@@ -649,10 +661,11 @@ void NrcCache::training_step_host(const float* h_in, const float* h_tgt, uint32_
     training_step(host_tin_.ptr, host_tgt_.ptr, B, true, s);
     if (loss_out) *loss_out = loss();
 }
-// en::NeuralRadianceCache::InferAndTrain (src/NeuralRadianceCache.cu:97-156) on HOST buffers in ONE call: the training records
-// travel first (they are small), the inference pipeline follows, the training steps are queued behind the last inference chunk
-// on the compute stream -- so they overlap the D2H copy of the last radiance chunks -- and the host waits once, at the end.
-// Inference reads the EMA weights of the previous frame, exactly like the reference's inference-then-train order.
+// en::NeuralRadianceCache::InferAndTrain (src/NeuralRadianceCache.cu:97-156) on HOST buffers in ONE call.  The reference runs
+// Inference() with the parameters of the previous frame and then Train(); the result of that order is kept, but not the serial
+// schedule: the inference pipeline (PCIe-bound: 20 B in + 12 B out per record) reads a device-to-device SNAPSHOT of the
+// pre-training parameters (28.5 MB, ~10 us), so the training steps -- whose records travel first, they are small -- run on their
+// own stream underneath the record transfers instead of behind them.  The host waits once, at the end.
 void NrcCache::infer_and_train_host(const float* h_in, float* h_out, uint32_t n, const float* h_tin, const float* h_tgt, uint32_t B,
                                     uint32_t n_batches, bool use_ema, float* loss_out) {
     const bool train = n_batches > 0 && B > 0;
@@ -663,21 +676,38 @@ void NrcCache::infer_and_train_host(const float* h_in, float* h_out, uint32_t n,
     const uint32_t chunk = (uint32_t)sm_count_ * 2 * 2 * 4 * kTile;
     const uint32_t n_chunks = (n + chunk - 1) / chunk;
     ensure_pipeline(n_chunks);
-    cudaEvent_t ev_prev = pipe_events_[2 * (size_t)n_chunks], ev_train = pipe_events_[2 * (size_t)n_chunks + 1], ev_done = pipe_events_[2 * (size_t)n_chunks + 2];
+    const size_t e0 = 2 * (size_t)n_chunks;
+    cudaEvent_t ev_prev = pipe_events_[e0], ev_train = pipe_events_[e0 + 1], ev_done = pipe_events_[e0 + 2], ev_snap = pipe_events_[e0 + 3], ev_trained = pipe_events_[e0 + 4];
+    const bool overlap = train && n > 0;
+    cudaStream_t ts = overlap ? train_stream_ : compute_stream_;
     NRCHPM_CUDA(cudaEventRecord(ev_prev, stream_));
     NRCHPM_CUDA(cudaStreamWaitEvent(compute_stream_, ev_prev, 0));
     NRCHPM_CUDA(cudaStreamWaitEvent(copy_in_stream_, ev_prev, 0));
+    if (overlap) {
+        infer_snapshot_.ensure(n_params_);
+        NRCHPM_CUDA(cudaMemcpyAsync(infer_snapshot_.ptr, use_ema ? ema16_.ptr : w16_.ptr, n_params_ * sizeof(__half), cudaMemcpyDeviceToDevice, compute_stream_));
+        NRCHPM_CUDA(cudaEventRecord(ev_snap, compute_stream_));
+        NRCHPM_CUDA(cudaStreamWaitEvent(train_stream_, ev_snap, 0));        // training overwrites what the snapshot copy reads
+        infer_params_override_ = infer_snapshot_.ptr;
+    }
     if (train) {
         NRCHPM_CUDA(cudaMemcpyAsync(host_tin_.ptr, h_tin, T * 5 * sizeof(float), cudaMemcpyHostToDevice, copy_in_stream_));
         NRCHPM_CUDA(cudaMemcpyAsync(host_tgt_.ptr, h_tgt, T * 3 * sizeof(float), cudaMemcpyHostToDevice, copy_in_stream_));
         NRCHPM_CUDA(cudaEventRecord(ev_train, copy_in_stream_));
     }
-    if (n) queue_inference_pipeline(h_in, h_out, n, use_ema, chunk, n_chunks);
+    try {
+        if (n) queue_inference_pipeline(h_in, h_out, n, use_ema, chunk, n_chunks);
+    } catch (...) { infer_params_override_ = nullptr; throw; }
+    infer_params_override_ = nullptr;
     if (train) {
-        NRCHPM_CUDA(cudaStreamWaitEvent(compute_stream_, ev_train, 0));
+        NRCHPM_CUDA(cudaStreamWaitEvent(ts, ev_train, 0));
         for (uint32_t b = 0; b < n_batches; b++)
-            training_step(host_tin_.ptr + (size_t)b * B * 5, host_tgt_.ptr + (size_t)b * B * 3, B, true, compute_stream_);
-        NRCHPM_CUDA(cudaMemcpyAsync(&loss_host_, loss_dev_.ptr, sizeof(float), cudaMemcpyDeviceToHost, compute_stream_));
+            training_step(host_tin_.ptr + (size_t)b * B * 5, host_tgt_.ptr + (size_t)b * B * 3, B, true, ts);
+        NRCHPM_CUDA(cudaMemcpyAsync(&loss_host_, loss_dev_.ptr, sizeof(float), cudaMemcpyDeviceToHost, ts));
+        if (overlap) {
+            NRCHPM_CUDA(cudaEventRecord(ev_trained, train_stream_));
+            NRCHPM_CUDA(cudaStreamWaitEvent(compute_stream_, ev_trained, 0));
+        }
     }
     // later work on the cache's own stream is ordered behind this call
     NRCHPM_CUDA(cudaEventRecord(ev_done, compute_stream_));

@@ -79,6 +79,7 @@ private:
     EncParams enc_;
     size_t n_mlp_ = 0, n_grid_ = 0, n_params_ = 0;
     int sm_count_ = 148;
+    size_t infer_smem_level_bytes() const;
     int infer_groups_ = 0, train_groups_ = 1;      // 256-thread groups per CTA of the two-threads-per-record kernels (0: one-thread kernels)
     DeviceBuffer<float> master_, m1_, m2_, loss_dev_, loss_partials_, dw_partials_, mlp_grad_f32_;
     DeviceBuffer<__half> w16_, ema16_, grad16_, x16_, acts_, dacts_, out16_, dout16_, dx16_;
@@ -96,6 +97,9 @@ private:
     cudaStream_t stream_ = nullptr;
     std::vector<std::pair<uint32_t, uint32_t>> infer_batches_;   // (first record, count)
     cudaStream_t copy_in_stream_ = nullptr, copy_out_stream_ = nullptr, compute_stream_ = nullptr;   // host-buffer pipeline
+    cudaStream_t train_stream_ = nullptr;            // InferAndTrain on host buffers: training overlaps the inference pipeline
+    DeviceBuffer<__half> infer_snapshot_;            // ... which then reads a snapshot of the pre-training parameters
+    const __half* infer_params_override_ = nullptr;
     std::vector<cudaEvent_t> pipe_events_;
 };
 

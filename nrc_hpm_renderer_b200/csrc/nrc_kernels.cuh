@@ -25,7 +25,21 @@
 #define NRC_GATHER_BITS 64
 #endif
 
+// cache operator of the hash-grid gather loads: 0 = default (L1-allocating), 1 = ld.global.cg (L2 only)
+#ifndef NRC_GATHER_CG
+#define NRC_GATHER_CG 0
+#endif
+
 namespace nrchpm {
+
+template <class T>
+__device__ __forceinline__ T gather_ld(const void* p) {
+#if NRC_GATHER_CG
+    return __ldcg(reinterpret_cast<const T*>(p));
+#else
+    return *reinterpret_cast<const T*>(p);
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------- encodings
 __device__ __forceinline__ float quartic_cdf(float x, float inv_radius) {      // common_device.h:905-920
@@ -41,6 +55,7 @@ struct GridLevel {
 };
 
 // grid.h:49-212 / common_device.h:632-718, 842-868: cell corners (entry indices relative to the level) and weights
+template <bool POW2 = false>
 __device__ __forceinline__ void grid_level_cell(const EncParams& e, int l, float x0, float x1, float x2, GridLevel& c) {
     const float scale = e.level_scale[l];
     float p[3] = {fmaf(scale, x0, 0.5f), fmaf(scale, x1, 0.5f), fmaf(scale, x2, 0.5f)};
@@ -53,7 +68,8 @@ __device__ __forceinline__ void grid_level_cell(const EncParams& e, int l, float
     }
     const uint32_t hs = e.level_hsize[l], s0 = e.level_s0[l], s1 = e.level_s1[l], s2 = e.level_s2[l];
     const bool hashed = e.level_hash[l] != 0;
-    const bool pow2 = (hs & (hs - 1)) == 0;        // `% hashmap_size` is a mask for power-of-two tables (every level of the presets)
+    // `% hashmap_size` is a mask for power-of-two tables (every level of the presets: POW2 instantiation, no division code)
+    const bool pow2 = POW2 || (hs & (hs - 1)) == 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         float w = 1;
@@ -62,9 +78,112 @@ __device__ __forceinline__ void grid_level_cell(const EncParams& e, int l, float
         for (int d = 0; d < 3; d++) {
             if ((k & (1 << d)) == 0) { w *= 1 - p[d]; q[d] = g[d]; } else { w *= p[d]; q[d] = g[d] + 1; }
         }
-        uint32_t index = hashed ? ((q[0] * 1u) ^ (q[1] * 2654435761u) ^ (q[2] * 805459861u)) : (q[0] * s0 + q[1] * s1 + q[2] * s2);
-        c.idx[k] = pow2 ? (index & (hs - 1)) : (index % hs);
+        const uint32_t ih = (q[0] * 1u) ^ (q[1] * 2654435761u) ^ (q[2] * 805459861u), il = q[0] * s0 + q[1] * s1 + q[2] * s2;
+        const uint32_t index = hashed ? ih : il;
+        if (POW2) c.idx[k] = index & (hs - 1);
+        else c.idx[k] = pow2 ? (index & (hs - 1)) : (index % hs);
         c.w[k] = w;
+    }
+}
+
+// one hash-grid level whose table has been staged in shared memory (inference kernel, coarse levels): the same corners, weights
+// and fp16 fma order as the global-memory path below; a divergent LDS costs its bank-conflict degree (~3-4 cycles per warp)
+// instead of one L1 wavefront per lane
+__device__ __forceinline__ __half2 encode_level_smem(const EncParams& e, int l, uint32_t table_smem_addr, float x0, float x1, float x2) {
+    GridLevel c;
+    grid_level_cell(e, l, x0, x1, x2, c);
+    __half2 r = __float2half2_rn(0.0f);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        uint32_t v;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(table_smem_addr + c.idx[k] * 4u));
+        r = __hfma2(__half2half2(__float2half_rn(c.w[k])), *reinterpret_cast<const __half2*>(&v), r);
+    }
+    return r;
+}
+
+// Hash-grid levels [l_begin, l_end), UNROLL levels per round: every gather of a round is issued before the first one is
+// consumed (the kernel is bound by the latency of these L2 round trips), so the body is branch-free -- one basic block of
+// predicated loads followed by one of fp16 fmas.  Gather diet (bit-exact):
+//  * a corner whose trilinear weight is exactly 0 contributes fma(0, v, r) == r, so its load is predicated off.  With the
+//    reference's position normalisation (coordinates ~30) the fractional part is 0 in every dimension at the
+//    finest level and often at the next ones: ~13 % of all gathers disappear;
+//  * the two corners of an x-edge sit in ONE aligned 8-byte word (16-byte group with NRC_GATHER_BITS == 128) whenever their
+//    indices differ only in the low bit(s) (dense levels and the coherent-prime hash, whose x prime is 1) -> one wide load
+//    instead of two 32-bit loads, i.e. one L1 wavefront instead of two for half (three quarters) of all edges;
+//  * tcnn's stride arithmetic wraps in uint32 for resolutions >= 2^16 (common_device.h:842-868): the z stride (and at the
+//    finest level the y stride too) is 0 modulo the table size, so corners k and k+4 (k and k+2) are the SAME entry.  The
+//    aliasing corners are never loaded; they take the value of their twin through a select.
+template <int UNROLL, bool POW2, class Put>
+__device__ __forceinline__ void hashgrid_levels(const EncParams& e, const __half2* __restrict__ grid, float x0, float x1, float x2,
+                                                int l_begin, int l_end, Put& put) {
+#if NRC_GATHER_BITS == 128
+    typedef uint4 wide_t;
+    constexpr uint32_t kGroupMask = 3u;
+#else
+    typedef uint2 wide_t;
+    constexpr uint32_t kGroupMask = 1u;
+#endif
+    for (int l0 = l_begin; l0 < l_end; l0 += UNROLL) {
+        GridLevel c[UNROLL];
+        wide_t q[UNROLL][4];
+        uint32_t a1[UNROLL][4];
+        bool dupz[UNROLL], dupy[UNROLL];
+        // ---- addresses and predicated loads of the whole round
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const bool on = l0 + u < l_end;
+            const int l = on ? l0 + u : l_end - 1;
+            grid_level_cell<POW2>(e, l, x0, x1, x2, c[u]);
+            const __half2* base = grid + e.level_offset[l];
+            const uint32_t hs_m = e.level_hsize[l] - 1u;
+            const bool lin = e.level_hash[l] == 0 && (e.level_hsize[l] & hs_m) == 0;
+            dupz[u] = lin && (e.level_s2[l] & hs_m) == 0;
+            dupy[u] = dupz[u] && (e.level_s1[l] & hs_m) == 0;
+#pragma unroll
+            for (int k = 0; k < 8; k += 2) {
+                const int j = k >> 1;
+                const uint32_t i0 = c[u].idx[k], i1 = c[u].idx[k + 1];
+                bool n0 = c[u].w[k] != 0.0f, n1 = c[u].w[k + 1] != 0.0f;
+                if (k < 4) { n0 |= dupz[u] & (c[u].w[k + 4] != 0.0f); n1 |= dupz[u] & (c[u].w[k + 5] != 0.0f); }
+                if (k == 0) { n0 |= dupy[u] & ((c[u].w[2] != 0.0f) | (c[u].w[6] != 0.0f)); n1 |= dupy[u] & ((c[u].w[3] != 0.0f) | (c[u].w[7] != 0.0f)); }
+                const bool alias = (k >= 4 && dupz[u]) || (k == 2 && dupy[u]);        // this edge is the twin of an earlier one
+                const bool paired = (i0 ^ i1) <= kGroupMask;
+                const bool ld_wide = on & !alias & (n0 | (paired & n1)), ld_one = on & !alias & !paired & n1;
+                wide_t w = wide_t();
+                if (ld_wide) w = gather_ld<wide_t>(base + (i0 & ~kGroupMask));
+                uint32_t s = 0u;
+                if (ld_one) s = gather_ld<uint32_t>(base + i1);
+                q[u][j] = w; a1[u][j] = s;
+            }
+        }
+        // ---- interpolation (grid.h:144-163: fp16 fma over the corners in index order)
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            __half2 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k += 2) {
+                const int j = k >> 1;
+                const uint32_t i0 = c[u].idx[k], i1 = c[u].idx[k + 1];
+                const bool paired = (i0 ^ i1) <= kGroupMask;
+#if NRC_GATHER_BITS == 128
+                const uint32_t b0 = (i0 & 2u) ? ((i0 & 1u) ? q[u][j].w : q[u][j].z) : ((i0 & 1u) ? q[u][j].y : q[u][j].x);
+                const uint32_t b1 = (i1 & 2u) ? ((i1 & 1u) ? q[u][j].w : q[u][j].z) : ((i1 & 1u) ? q[u][j].y : q[u][j].x);
+#else
+                const uint32_t b0 = (i0 & 1u) ? q[u][j].y : q[u][j].x;
+                const uint32_t b1 = (i1 & 1u) ? q[u][j].y : q[u][j].x;
+#endif
+                const uint32_t b1s = paired ? b1 : a1[u][j];
+                v[k] = *reinterpret_cast<const __half2*>(&b0);
+                v[k + 1] = *reinterpret_cast<const __half2*>(&b1s);
+            }
+            if (dupy[u]) { v[2] = v[0]; v[3] = v[1]; }
+            if (dupz[u]) { v[4] = v[0]; v[5] = v[1]; v[6] = v[2]; v[7] = v[3]; }
+            __half2 r = __float2half2_rn(0.0f);
+#pragma unroll
+            for (int k = 0; k < 8; k++) r = __hfma2(__half2half2(__float2half_rn(c[u].w[k])), v[k], r);
+            if (l0 + u < l_end) put.put2(2 * (l0 + u), r);
+        }
     }
 }
 
@@ -74,63 +193,8 @@ template <int UNROLL = 2, class Put>
 __device__ __forceinline__ void encode_position(const EncParams& e, const __half2* __restrict__ grid, float x0, float x1, float x2,
                                                 int l_begin, int l_end, Put& put) {
     if (e.pos_enc == POS_HASHGRID) {
-#pragma unroll UNROLL
-        for (int l = l_begin; l < l_end; l++) {
-            GridLevel c;
-            grid_level_cell(e, l, x0, x1, x2, c);
-            const __half2* base = grid + e.level_offset[l];
-            // Gather diet (bit-exact):
-            //  * a corner whose trilinear weight is exactly 0 contributes fma(0, v, r) == r, so its load is skipped.  With the
-            //    reference's position normalisation (coordinates ~30) the fractional part is 0 in every
-            //    dimension at the finest level and often at the next ones: ~13 % of all gathers disappear;
-            //  * the two corners of an x-edge sit in ONE aligned 8-byte word whenever their indices differ only in bit 0
-            //    (dense levels: x even; coherent-prime hash, whose x prime is 1: x even) -> one 64-bit load instead of
-            //    two 32-bit loads, i.e. one L1 wavefront instead of two for half of all edges.
-            //  * tcnn's stride arithmetic wraps in uint32 for resolutions >= 2^16 (common_device.h:842-868): the z stride (and at
-            //    the finest level the y stride too) is 0 modulo the table size, so corners k and k+4 (k and k+2) are the SAME
-            //    entry.  That is a per-level constant, hence a warp-uniform branch: the aliasing corners reuse the loaded value.
-            const uint32_t hs_m = e.level_hsize[l] - 1u;
-            const bool lin = e.level_hash[l] == 0 && (e.level_hsize[l] & hs_m) == 0;
-            const bool dupz = lin && (e.level_s2[l] & hs_m) == 0;
-            const bool dupy = dupz && (e.level_s1[l] & hs_m) == 0;
-            __half2 v[8];
-#pragma unroll
-            for (int k = 0; k < 8; k += 2) {
-                if ((k >= 4 && dupz) || (k == 2 && dupy)) { v[k] = v[k & (k >= 4 ? 3 : 1)]; v[k + 1] = v[(k + 1) & (k >= 4 ? 3 : 1)]; continue; }
-                const uint32_t i0 = c.idx[k], i1 = c.idx[k + 1];
-                bool n0 = c.w[k] != 0.0f, n1 = c.w[k + 1] != 0.0f;
-                if (k < 4 && dupz) { n0 |= c.w[k + 4] != 0.0f; n1 |= c.w[k + 5] != 0.0f; }
-                if (k == 0 && dupy) { n0 |= (c.w[2] != 0.0f) | (c.w[6] != 0.0f); n1 |= (c.w[3] != 0.0f) | (c.w[7] != 0.0f); }
-#if NRC_GATHER_BITS == 128
-                // 128-bit flavour: the aligned group of four entries holds both corners for three of four x positions
-                // (x mod 4 != 3), so only a quarter of the edges need the second load -- 1.25 L1 wavefronts per edge, not 1.5
-                const bool paired = (i0 ^ i1) < 4u;
-                uint4 q = make_uint4(0u, 0u, 0u, 0u);
-                if (n0 | (paired & n1)) q = *reinterpret_cast<const uint4*>(base + (i0 & ~3u));
-                uint32_t a1 = 0u;
-                if (!paired & n1) a1 = *reinterpret_cast<const uint32_t*>(base + i1);
-                const uint32_t a0 = (i0 & 2u) ? ((i0 & 1u) ? q.w : q.z) : ((i0 & 1u) ? q.y : q.x);
-                const uint32_t a1q = (i1 & 2u) ? ((i1 & 1u) ? q.w : q.z) : ((i1 & 1u) ? q.y : q.x);
-                a1 = paired ? a1q : a1;
-#else
-                const bool paired = (i0 ^ i1) == 1u;
-                // predicated, branch-free: one 64-bit load of the aligned word holding corner 0 (and corner 1 when paired),
-                // plus a 32-bit load of corner 1 only when it lives elsewhere
-                uint2 q = make_uint2(0u, 0u);
-                if (n0 | (paired & n1)) q = *reinterpret_cast<const uint2*>(base + (i0 & ~1u));
-                uint32_t a1 = 0u;
-                if (!paired & n1) a1 = *reinterpret_cast<const uint32_t*>(base + i1);
-                const uint32_t a0 = (i0 & 1u) ? q.y : q.x;
-                a1 = paired ? ((i1 & 1u) ? q.y : q.x) : a1;
-#endif
-                v[k] = *reinterpret_cast<const __half2*>(&a0);
-                v[k + 1] = *reinterpret_cast<const __half2*>(&a1);
-            }
-            __half2 r = __float2half2_rn(0.0f);
-#pragma unroll
-            for (int k = 0; k < 8; k++) r = __hfma2(__half2half2(__float2half_rn(c.w[k])), v[k], r);   // grid.h:144-163: fp16 fma
-            put.put2(2 * l, r);
-        }
+        if (e.all_pow2) hashgrid_levels<UNROLL, true>(e, grid, x0, x1, x2, l_begin, l_end, put);
+        else hashgrid_levels<UNROLL, false>(e, grid, x0, x1, x2, l_begin, l_end, put);
     } else if (e.pos_enc == POS_IDENTITY) {
         put.put(0, __float2half_rn(x0)); put.put(1, __float2half_rn(x1)); put.put(2, __float2half_rn(x2));
     } else if (e.pos_enc == POS_TRIANGLE) {
@@ -290,6 +354,8 @@ struct FwdArgs {
     const uint32_t* d_count;    // optional device-side record count (<= n)
     uint32_t n;
     float* out;                 // inference: float[*][3]
+    uint32_t smem_levels;       // inference: the first `smem_levels` hash-grid levels (`smem_level_entries` entries) are staged in smem
+    uint32_t smem_level_entries;
     // training only
     const float* target;        // float[n][3]
     __half* x16;                // [n][IN_W]   network input
@@ -313,6 +379,9 @@ constexpr uint32_t kColD = 0, kColA = 96, kColsPerWg = 128;
 #endif
 #ifndef NRC_INFER_UNROLL
 #define NRC_INFER_UNROLL 2
+#endif
+#ifndef NRC_SMEM_LEVELS
+#define NRC_SMEM_LEVELS 0            // coarse hash-grid levels staged in shared memory by the inference kernel
 #endif
 constexpr int kInferWgs = NRC_INFER_WGS, kInferCtas = NRC_INFER_CTAS;
 __host__ __device__ constexpr uint32_t fwd_wg_stride(int wgs) { return wgs * 128 <= 512 ? 128u : 96u; }
@@ -340,9 +409,14 @@ __global__ void __launch_bounds__(TRAIN ? kFwdThreads : kInferWgs * 128, TRAIN ?
     uint8_t* wh_s = w0_s + IN_W * 128;
     uint8_t* wo_s = wh_s + (H - 1) * 8192;
     uint8_t* x_s = wo_s + 2048 + wg * (IN_W * 256);
+    uint8_t* lvl_s = wo_s + 2048 + nwg * (IN_W * 256);          // staged coarse hash-grid levels (inference only)
 
     if (warp == 0) { tmem_alloc(&tmem_base_s, kAlloc); tmem_relinquish(); }
     if (tid == 0) { for (int g = 0; g < kMaxWg; g++) mbar_init(&mbar[g], 1); fence_mbar_init(); }
+    if (NRC_SMEM_LEVELS > 0 && !TRAIN && a.smem_levels) {
+        const int4* src = reinterpret_cast<const int4*>(a.params + a.n_mlp);
+        for (uint32_t c = tid; c < a.smem_level_entries / 4; c += nthreads) reinterpret_cast<int4*>(lvl_s)[c] = src[c];
+    }
     copy_weights_kmajor(w0_s, a.params, kWidth, IN_W, tid, nthreads);
     for (int l = 1; l < H; l++) copy_weights_kmajor(wh_s + (l - 1) * 8192, a.params + IN_W * kWidth + (l - 1) * kWidth * kWidth, kWidth, kWidth, tid, nthreads);
     copy_weights_kmajor(wo_s, a.params + IN_W * kWidth + (H - 1) * kWidth * kWidth, kOutPad, kWidth, tid, nthreads);
@@ -375,7 +449,14 @@ __global__ void __launch_bounds__(TRAIN ? kFwdThreads : kInferWgs * 128, TRAIN ?
         }
         uint8_t* my_row = x_s + (r >> 3) * (IN_W * 16) + (r & 7) * 16;
         SmemRowPut put{my_row};
-        encode_record<TRAIN ? 2 : NRC_INFER_UNROLL>(a.enc, grid, x0, x1, x2, th, ph, put);
+        if (NRC_SMEM_LEVELS > 0 && !TRAIN && a.smem_levels) {
+            const uint32_t lvl_addr = smem_u32(lvl_s);
+            for (uint32_t l = 0; l < a.smem_levels; l++) put.put2(2 * l, encode_level_smem(a.enc, l, lvl_addr + a.enc.level_offset[l] * 4u, x0, x1, x2));
+            encode_position<NRC_INFER_UNROLL>(a.enc, grid, x0, x1, x2, (int)a.smem_levels, a.enc.n_levels, put);
+            encode_direction_pad(a.enc, th, ph, put);
+        } else {
+            encode_record<TRAIN ? 2 : NRC_INFER_UNROLL>(a.enc, grid, x0, x1, x2, th, ph, put);
+        }
         fence_proxy_async_smem();
         fence_before();
         named_bar_sync(1 + wg, 128);

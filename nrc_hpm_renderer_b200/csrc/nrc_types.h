@@ -24,6 +24,7 @@ struct EncParams {
     uint32_t level_offset[kMaxLevels];   // in grid entries (half2)
     uint32_t level_s0[kMaxLevels], level_s1[kMaxLevels], level_s2[kMaxLevels];   // dense strides with tcnn's uint32 wrap-around
     uint32_t level_hash[kMaxLevels];
+    int all_pow2;       // every level's table size is a power of two (`% size` is a mask)
 };
 
 // Adam state of ONE hash-grid entry (two fp16 features): fp32 master weights, first / second moments and the per-parameter

@@ -19,6 +19,10 @@ def run(infer_groups, train_groups, ref_out=None, n_infer=N_INFER, iters=20):
     d_out = [torch.empty((n_infer, 3), dtype=torch.float32, device="cuda") for _ in range(4)]
     tin = [torch.from_numpy(synth_records(rng, TRAIN_BATCH)).cuda() for _ in range(8)]
     tgt = [torch.from_numpy((rng.random((TRAIN_BATCH, 3), dtype=np.float32) * 2).astype(np.float32)).cuda() for _ in range(8)]
+    nrc.inference(d_in[0], d_out[0], n_infer, False, sp)           # initial working weights: deterministic, identical for every variant
+    torch.cuda.synchronize()
+    o = d_out[0].cpu().numpy()
+    crc0 = int(np.bitwise_xor.reduce(o.view(np.uint32).ravel().astype(np.uint64) * np.arange(1, o.size + 1, dtype=np.uint64)) & np.uint64(0xFFFFFFFF))
     losses = []
     for i in range(8):
         nrc.training_step(tin[i], tgt[i], TRAIN_BATCH, True, sp); losses.append(nrc.GetLoss())
@@ -37,7 +41,8 @@ def run(infer_groups, train_groups, ref_out=None, n_infer=N_INFER, iters=20):
         nrc.training_step(tin[i % 8], tgt[i % 8], TRAIN_BATCH, True, sp)
     e1.record(st); torch.cuda.synchronize()
     t_tr = e0.elapsed_time(e1) / 200
-    res = {"infer_groups": infer_groups, "train_groups": train_groups, "infer_ms": round(t_inf, 4), "train_step_us": round(t_tr * 1e3, 1), "loss8": losses[-1]}
+    res = {"infer_groups": infer_groups, "train_groups": train_groups, "infer_ms": round(t_inf, 4), "train_step_us": round(t_tr * 1e3, 1), "loss8": losses[-1],
+           "out_crc_initial_weights": crc0}
     if ref_out is not None:
         res["max_abs_diff_vs_ref"] = float(np.nanmax(np.abs(out0 - ref_out)))
     nrc.Destroy()
