@@ -128,6 +128,11 @@ void NrcCache::derive() {
             for (uint32_t dim = 0; dim < 3 && stride <= p; ++dim) { s[dim] = stride; stride *= res; }
             e.level_s0[i] = s[0]; e.level_s1[i] = s[1]; e.level_s2[i] = s[2];
             e.level_hash[i] = p < stride ? 1u : 0u;
+            {   // kind of index arithmetic (nrc_kernels.cuh: hashgrid_pipelined); "generic" covers wrapped strides and odd table sizes
+                const bool pow2 = (p & (p - 1)) == 0;
+                const bool dup = !e.level_hash[i] && pow2 && ((s[2] & (p - 1)) == 0 || (s[1] & (p - 1)) == 0);
+                e.level_kind[i] = e.level_hash[i] ? 2u : (dup || !pow2) ? 0u : 1u;
+            }
             offset += p;
         }
         n_grid_ = (size_t)offset * 2;

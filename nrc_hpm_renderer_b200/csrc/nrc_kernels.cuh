@@ -30,6 +30,18 @@
 #define NRC_GATHER_CG 0
 #endif
 
+// 1: software-pipelined hash-grid gathers (level l+1 in flight while level l is interpolated); 0: rounds of NRC_INFER_UNROLL levels.
+// Measured on B200, 2 073 600 random records (profiles/r01_summary.md): rounds of ONE level 0.636 ms, rounds of two 0.720 ms,
+// pipelined 0.698 ms, 128-bit groups 0.664 ms -- the more gathers are in flight, the more 128-byte lines the small L1 (84 KB next
+// to 144 KB of shared memory) has to hold and the fewer second-corner loads still find the sector of their twin (L1 hit rate 30 %
+// -> 15 %), which turns into extra L1->L2 requests, the unit this kernel saturates first.  Hence the default: one level per round.
+#ifndef NRC_GATHER_PIPE
+#define NRC_GATHER_PIPE 0
+#endif
+#ifndef NRC_TRAIN_UNROLL
+#define NRC_TRAIN_UNROLL 2           // levels per round in the (latency-bound, low-occupancy) training forward kernel
+#endif
+
 namespace nrchpm {
 
 template <class T>
@@ -187,14 +199,140 @@ __device__ __forceinline__ void hashgrid_levels(const EncParams& e, const __half
     }
 }
 
+// ---- software-pipelined flavour (power-of-two tables, i.e. every preset): the gathers of level l+1 are in flight while level l
+// is interpolated and the addresses of level l+2 are computed, so a warp overlaps its own address arithmetic (~150 instructions
+// per level) with its own L2 round trips -- there are only four warps per scheduler to hide them otherwise (TMEM caps the
+// resident tiles).  Levels are processed in runs of one KIND so that the index arithmetic carries no per-level selects:
+// 1 = dense (x + y*s1 + z*s2), 2 = hashed (x ^ y*P1 ^ z*P2), 0 = generic (strides wrapped in uint32: aliasing corners).
+struct LevelLoads {
+    float f[3];          // fractional cell position
+    uint32_t sel;        // bit j: low index bit of corner 2j, bit 4+j: of corner 2j+1, bit 8+j: both in one 8-byte word, bits 12/13: dupz/dupy
+    uint2 q[4];          // aligned 8-byte word of edge j (corners 2j, 2j+1)
+    uint32_t a1[4];      // corner 2j+1 when it lives elsewhere
+};
+
+template <int KIND>
+__device__ __forceinline__ void level_issue(const EncParams& e, const __half2* __restrict__ grid, int l, float x0, float x1, float x2, LevelLoads& s) {
+    const float scale = e.level_scale[l];
+    float p[3] = {fmaf(scale, x0, 0.5f), fmaf(scale, x1, 0.5f), fmaf(scale, x2, 0.5f)};
+    uint32_t g[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const float t = floorf(p[d]);
+        g[d] = (uint32_t)(int)t;
+        s.f[d] = p[d] - t;
+    }
+    const uint32_t m = e.level_hsize[l] - 1u;
+    const __half2* base = grid + e.level_offset[l];
+    uint32_t h[4];       // index contribution of the four (y, z) corner combinations
+    bool dupz = false, dupy = false;
+    if (KIND == 2) {
+        const uint32_t hy0 = g[1] * 2654435761u, hy1 = hy0 + 2654435761u, hz0 = g[2] * 805459861u, hz1 = hz0 + 805459861u;
+        h[0] = hy0 ^ hz0; h[1] = hy1 ^ hz0; h[2] = hy0 ^ hz1; h[3] = hy1 ^ hz1;
+    } else if (KIND == 1) {
+        const uint32_t s1 = e.level_s1[l], s2 = e.level_s2[l], a = g[1] * s1 + g[2] * s2;
+        h[0] = a; h[1] = a + s1; h[2] = a + s2; h[3] = a + s1 + s2;
+    } else {
+        const bool hashed = e.level_hash[l] != 0;
+        const uint32_t s1 = e.level_s1[l], s2 = e.level_s2[l], a = g[1] * s1 + g[2] * s2;
+        const uint32_t hy0 = g[1] * 2654435761u, hy1 = hy0 + 2654435761u, hz0 = g[2] * 805459861u, hz1 = hz0 + 805459861u;
+        h[0] = hashed ? hy0 ^ hz0 : a; h[1] = hashed ? hy1 ^ hz0 : a + s1; h[2] = hashed ? hy0 ^ hz1 : a + s2; h[3] = hashed ? hy1 ^ hz1 : a + s1 + s2;
+        dupz = !hashed && (s2 & m) == 0;
+        dupy = dupz && (s1 & m) == 0;
+    }
+    const bool hashed_x = KIND == 2 || (KIND == 0 && e.level_hash[l] != 0);
+    // a corner whose weight is exactly 0 is not loaded: the weight is a product of three factors f or 1 - f
+    const bool zx[2] = {1.0f - s.f[0] != 0.0f, s.f[0] != 0.0f}, zy[2] = {1.0f - s.f[1] != 0.0f, s.f[1] != 0.0f}, zz[2] = {1.0f - s.f[2] != 0.0f, s.f[2] != 0.0f};
+    uint32_t sel = (dupz ? 1u << 12 : 0u) | (dupy ? 1u << 13 : 0u);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t i0 = (hashed_x ? (g[0] ^ h[j]) : (g[0] + h[j])) & m, i1 = (hashed_x ? ((g[0] + 1u) ^ h[j]) : (g[0] + 1u + h[j])) & m;
+        bool nyz = zy[j & 1] & zz[j >> 1];
+        if (KIND == 0) {                                                     // twins of this edge that alias onto it
+            if (j < 2) nyz |= dupz & zy[j & 1] & zz[1];
+            if (j == 0) nyz |= dupy & (zy[1] & (zz[0] | zz[1]));
+        }
+        const bool alias = KIND == 0 && ((j >= 2 && dupz) || (j == 1 && dupy));
+        const bool n0 = zx[0] & nyz, n1 = zx[1] & nyz;
+        const bool paired = (i0 ^ i1) <= 1u;
+        sel |= (i0 & 1u) << j | (i1 & 1u) << (4 + j) | (paired ? 1u : 0u) << (8 + j);
+        uint2 w = make_uint2(0u, 0u);
+        if (!alias & (n0 | (paired & n1))) w = gather_ld<uint2>(base + (i0 & ~1u));
+        uint32_t o = 0u;
+        if (!alias & !paired & n1) o = gather_ld<uint32_t>(base + i1);
+        s.q[j] = w; s.a1[j] = o;
+    }
+    s.sel = sel;
+}
+
+// grid.h:144-163: fp16 fma over the eight corners in index order, weights computed in fp32 as (fx * fy) * fz
+template <int KIND>
+__device__ __forceinline__ __half2 level_finish(const LevelLoads& s) {
+    __half2 v[8];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t b0 = (s.sel >> j & 1u) ? s.q[j].y : s.q[j].x;
+        const uint32_t b1 = (s.sel >> (4 + j) & 1u) ? s.q[j].y : s.q[j].x;
+        const uint32_t b1s = (s.sel >> (8 + j) & 1u) ? b1 : s.a1[j];
+        v[2 * j] = *reinterpret_cast<const __half2*>(&b0);
+        v[2 * j + 1] = *reinterpret_cast<const __half2*>(&b1s);
+    }
+    if (KIND == 0) {
+        if (s.sel >> 13 & 1u) { v[2] = v[0]; v[3] = v[1]; }
+        if (s.sel >> 12 & 1u) { v[4] = v[0]; v[5] = v[1]; v[6] = v[2]; v[7] = v[3]; }
+    }
+    const float fx[2] = {1.0f - s.f[0], s.f[0]}, fy[2] = {1.0f - s.f[1], s.f[1]}, fz[2] = {1.0f - s.f[2], s.f[2]};
+    __half2 r = __float2half2_rn(0.0f);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const float w = ((1.0f * fx[k & 1]) * fy[(k >> 1) & 1]) * fz[k >> 2];
+        r = __hfma2(__half2half2(__float2half_rn(w)), v[k], r);
+    }
+    return r;
+}
+
+template <int KIND, class Put>
+__device__ __forceinline__ void hashgrid_run(const EncParams& e, const __half2* __restrict__ grid, float x0, float x1, float x2, int lb, int le, Put& put) {
+    LevelLoads A, B;
+    level_issue<KIND>(e, grid, lb, x0, x1, x2, A);
+    for (int l = lb; l < le; l += 2) {
+        const bool has_b = l + 1 < le;
+        if (has_b) level_issue<KIND>(e, grid, l + 1, x0, x1, x2, B);
+        put.put2(2 * l, level_finish<KIND>(A));
+        if (has_b) {
+            if (l + 2 < le) level_issue<KIND>(e, grid, l + 2, x0, x1, x2, A);
+            put.put2(2 * (l + 1), level_finish<KIND>(B));
+        }
+    }
+}
+
+template <class Put>
+__device__ __forceinline__ void hashgrid_pipelined(const EncParams& e, const __half2* __restrict__ grid, float x0, float x1, float x2,
+                                                   int l_begin, int l_end, Put& put) {
+    int l = l_begin;
+    while (l < l_end) {
+        const uint32_t kind = e.level_kind[l];
+        int r = l + 1;
+        while (r < l_end && e.level_kind[r] == kind) r++;
+        if (kind == 2) hashgrid_run<2>(e, grid, x0, x1, x2, l, r, put);
+        else if (kind == 1) hashgrid_run<1>(e, grid, x0, x1, x2, l, r, put);
+        else hashgrid_run<0>(e, grid, x0, x1, x2, l, r, put);
+        l = r;
+    }
+}
+
 // put(k, half) / put2(k_even, half2) receive feature k of this record.
 // Position features: hash-grid levels [l_begin, l_end) -- the whole encoding for the other (parameter-free) encoders.
+// UNROLL > 0: rounds of UNROLL levels; UNROLL == 0: the software-pipelined flavour (needs ~128 registers: inference kernel only)
 template <int UNROLL = 2, class Put>
 __device__ __forceinline__ void encode_position(const EncParams& e, const __half2* __restrict__ grid, float x0, float x1, float x2,
                                                 int l_begin, int l_end, Put& put) {
     if (e.pos_enc == POS_HASHGRID) {
-        if (e.all_pow2) hashgrid_levels<UNROLL, true>(e, grid, x0, x1, x2, l_begin, l_end, put);
-        else hashgrid_levels<UNROLL, false>(e, grid, x0, x1, x2, l_begin, l_end, put);
+        constexpr int U = UNROLL > 0 ? UNROLL : 2;
+        if (e.all_pow2) {
+            if (UNROLL == 0) hashgrid_pipelined(e, grid, x0, x1, x2, l_begin, l_end, put);
+            else hashgrid_levels<U, true>(e, grid, x0, x1, x2, l_begin, l_end, put);
+        } else hashgrid_levels<U, false>(e, grid, x0, x1, x2, l_begin, l_end, put);
     } else if (e.pos_enc == POS_IDENTITY) {
         put.put(0, __float2half_rn(x0)); put.put(1, __float2half_rn(x1)); put.put(2, __float2half_rn(x2));
     } else if (e.pos_enc == POS_TRIANGLE) {
@@ -378,7 +516,7 @@ constexpr uint32_t kColD = 0, kColA = 96, kColsPerWg = 128;
 #define NRC_INFER_CTAS 2
 #endif
 #ifndef NRC_INFER_UNROLL
-#define NRC_INFER_UNROLL 2
+#define NRC_INFER_UNROLL (NRC_GATHER_PIPE ? 0 : 1)
 #endif
 #ifndef NRC_SMEM_LEVELS
 #define NRC_SMEM_LEVELS 0            // coarse hash-grid levels staged in shared memory by the inference kernel
@@ -806,7 +944,7 @@ __global__ void __launch_bounds__(TRAIN ? 256 : 768, TRAIN ? 2 : 1) nrc_forward2
         SmemRowPut put{my_row};
         {   // one call site (code size: each CTA runs this once in the 128-tile training batch, instruction fetch is cold)
             const int lb = half == 0 ? 0 : l_split, le = (half == 0 || !hashgrid) ? l_split : a.enc.n_levels;
-            if (half == 0 || hashgrid) encode_position<TRAIN ? 4 : 2>(a.enc, grid, x0, x1, x2, lb, le, put);
+            if (half == 0 || hashgrid) encode_position<TRAIN ? NRC_TRAIN_UNROLL : 2>(a.enc, grid, x0, x1, x2, lb, le, put);
             if (half == 1) encode_direction_pad(a.enc, th, ph, put);
         }
         if (weights_pending) { cp_async_wait_all(); fence_proxy_async_smem(); mbar_arrive(&wbar); }

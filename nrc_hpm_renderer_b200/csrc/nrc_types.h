@@ -24,6 +24,7 @@ struct EncParams {
     uint32_t level_offset[kMaxLevels];   // in grid entries (half2)
     uint32_t level_s0[kMaxLevels], level_s1[kMaxLevels], level_s2[kMaxLevels];   // dense strides with tcnn's uint32 wrap-around
     uint32_t level_hash[kMaxLevels];
+    uint32_t level_kind[kMaxLevels];     // 1 dense, 2 hashed, 0 generic (uint32-wrapped strides: aliasing corners)
     int all_pow2;       // every level's table size is a power of two (`% size` is a mask)
 };
 

@@ -146,6 +146,8 @@ struct Ctx {
     V3 new_ray_dir(V3 old_dir, bool phase_sampling) {                // dir_gen.glsl:22-64
         old_dir = normalize3(old_dir);
         V3 ortho = old_dir.z < old_dir.x ? V3{old_dir.y, -old_dir.x, 0.0f} : V3{0.0f, -old_dir.z, old_dir.y};
+        // degenerate axis (old_dir exactly (-1,0,0) or (0,0,-1)): normalize(0) is undefined in GLSL; see DESIGN.md section 4
+        if (ortho.x == 0.0f && ortho.y == 0.0f && ortho.z == 0.0f) ortho = V3{0.0f, 1.0f, 0.0f};
         ortho = normalize3(ortho);
         float angle;
         if (phase_sampling) {

@@ -125,7 +125,7 @@ def test_reference_class_round_trip(tmp_path):
         res = ref.CompareMc(mc, cam, rng.random(4).astype(np.float32))
     assert mc.camera is cam                                                                   # camera restored
     assert res.validPixelCount == int((ref.m_RefImage[..., 3] != 0).sum())
-    assert abs(res.GetRelBias()) < 0.1 and res.mse < res.refMean ** 2
+    assert np.isfinite([res.mse, res.ownVar]).all() and abs(res.GetRelBias()) < 0.1        # same estimator, same camera: unbiased
     p = str(tmp_path / "out.exr")
     mc.ExportOutputImageToFile(p)
     assert np.array_equal(exr.read_exr(p), mc.GetImage())

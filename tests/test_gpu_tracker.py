@@ -144,28 +144,42 @@ def test_mc_render_vs_oracle(oracle_lib):
 
 
 def test_frame_compact_equals_reference_mode(oracle_lib):
-    """Render() with warp-compacted inference == Render() in reference mode (host filter, all records), pixel for pixel;
-    frame 0 shows the primary estimate only because the EMA weights are still zero (Q7)."""
+    """Render() with warp-compacted inference == Render() in reference mode (host filter, all records), pixel for pixel, for the
+    same cache parameters.  Frame 0 shows the primary estimate only because the EMA weights are still zero (Q7).  Across *training*
+    frames the two modes may drift apart in the last bits: the hash-grid gradient is summed with fp16 atomics whose order depends on
+    what ran before (same property as tcnn's kernel_grid_backward) and Adam's first steps amplify a sign flip of a ~0 gradient; so
+    trained frames are compared statistically and the exact comparison is made with the parameters copied across and train=false."""
     from nrc_hpm_renderer_b200 import AppConfig, renderer as R
-    from nrc_hpm_renderer_b200.nrc import NeuralRadianceCache
+    from nrc_hpm_renderer_b200 import nrc as N
     W, H = 128, 64
-    imgs = []
+    imgs, caches, renderers = [], [], []
     for compact in (True, False):
         app = AppConfig.default(); app.log2_train_batch_size, app.train_batch_count, app.log2_infer_batch_size = 9, 2, 12
-        nrc = NeuralRadianceCache(app)
+        nrc = N.NeuralRadianceCache(app)
         r, *_ = setup(0, W, H, oracle_lib, train_pixels=1024, compact=compact, nrc=nrc)
         frames = []
         for f in range(3):
             r.Render(True, FR + np.float32(0.05 * f))
             frames.append(r.GetImage().copy())
-        imgs.append(frames)
+        imgs.append(frames); caches.append(nrc); renderers.append(r)
         ms = r.EvaluateTimestampQueries()
         assert ms["total"] > 0 and ms["gen_rays"] > 0
         assert np.isfinite(nrc.GetLoss())
-        prim = r.read(R.BUF_PRIMARY_COLOR).reshape(H, W, 4)
         if compact:
             assert np.all((frames[0][..., :3] >= 0) | np.isnan(frames[0][..., :3]))
-    for a, b in zip(*imgs):
-        assert np.array_equal(a, b, equal_nan=True)
+    assert np.array_equal(imgs[0][0], imgs[1][0], equal_nan=True)                 # frame 0: no cache term yet, bit-identical
+    for a, b in zip(imgs[0][1:], imgs[1][1:]):                                    # trained frames: same up to atomic-order drift
+        d = np.abs(a - b)[np.isfinite(a) & np.isfinite(b)]
+        assert d.mean() <= 2e-3 and d.max() <= 0.2, (d.mean(), d.max())
+    # identical parameters, no training: the two inference modes must agree bit for bit
+    caches[1].set_params(caches[0].get_params(N.MASTER))
+    caches[1].set_ema(caches[0].get_params(N.EMA))
+    fr = FR + np.float32(0.3)
+    for r in renderers:
+        r.Render(False, fr)
+    a, b = renderers[0].GetImage(), renderers[1].GetImage()
+    assert np.array_equal(a, b, equal_nan=True)
+    prim = renderers[0].read(R.BUF_PRIMARY_COLOR).reshape(H, W, 4)
+    assert np.any(a[..., :3] != prim[..., :3])                                    # the cache term is really there
     # frame 0: NRC output is exactly zero -> image == primary estimate; later frames add a non-negative cache term
     assert np.any(imgs[0][2] != imgs[0][0])

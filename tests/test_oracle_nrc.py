@@ -97,3 +97,18 @@ def test_adam_ema_step_against_tcnn(oracle_lib):
     assert np.max(np.abs(e1[:nm][sure] - z["ema_step1_mlp"].astype(np.float32)[sure])) <= 2e-3
     steps = m.get(m.STEPS)
     assert np.all(steps[:nm] == 1)
+
+
+def test_1000_step_curves_of_the_oracle_bracket_the_tolerance():
+    """The window tolerance of tests/test_gpu_loss_curve.py is the measured distance between faithful restatements: the oracle's
+    1000-step curves (fp16- and fp32-accumulation mode, recorded once -- 275 s each -- into oracle_loss1000_tri_ob_d5.npz) against
+    the reference's own tiny-cuda-nn curve (tcnn_loss1000_tri_ob_d5.npz)."""
+    o = golden("oracle_loss1000_tri_ob_d5.npz")
+    ref = golden("tcnn_loss1000_tri_ob_d5.npz")["losses"]
+    w = 50
+    for key, first2, worst, mean in (("oracle_fp16_accum", 0.01, 0.20, 0.09), ("oracle_fp32_accum", 0.01, 0.32, 0.12)):
+        cur = o[key]
+        assert abs(cur[0] - ref[0]) <= 1e-3 * ref[0]
+        ln = np.array([np.log(cur[i:i + w].mean() / ref[i:i + w].mean()) for i in range(0, len(ref), w)])
+        assert np.abs(ln[:2]).max() <= first2 and np.abs(ln).max() <= worst and np.abs(ln).mean() <= mean, (key, ln)
+        assert cur[-w:].mean() < 0.01 * cur[:w].mean()                                   # the curve falls > 100x
