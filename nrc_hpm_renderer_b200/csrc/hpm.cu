@@ -32,6 +32,10 @@ Renderer::Renderer(Scene* scene, NrcCache* nrc, const hpm_render_config& cfg, cu
     NRCHPM_REQUIRE(scene, "renderer: null scene");
     NRCHPM_REQUIRE(cfg.width > 0 && cfg.height > 0, "renderer: bad resolution");
     NRCHPM_REQUIRE(cfg.infer_batch_size > 0, "renderer: infer_batch_size must be > 0");
+    // the filter has one flag per inference batch of the cache (nrc-descriptors.glsl nrcInferFilter, NeuralRadianceCache.cu:136-144):
+    // both sides take INFER_BATCH_SIZE from the same AppConfig in the reference, a mismatch would silently skip batches
+    NRCHPM_REQUIRE(!nrc || cfg.compact_inference || cfg.infer_batch_size == nrc->config().infer_batch_size,
+                   "renderer: infer_batch_size differs from the NeuralRadianceCache's (both come from one AppConfig)");
     if (cfg_.x_end == 0) { cfg_.x_begin = 0; cfg_.x_end = cfg_.width; }
     NRCHPM_REQUIRE(cfg_.x_begin < cfg_.x_end && cfg_.x_end <= cfg_.width, "renderer: bad column strip");
     n_pixels_ = cfg_.width * cfg_.height;

@@ -624,7 +624,11 @@ void NrcCache::ensure_pipeline(uint32_t n_chunks) {
         NRCHPM_CUDA(cudaStreamCreateWithFlags(&copy_in_stream_, cudaStreamNonBlocking));
         NRCHPM_CUDA(cudaStreamCreateWithFlags(&copy_out_stream_, cudaStreamNonBlocking));
         NRCHPM_CUDA(cudaStreamCreateWithFlags(&compute_stream_, cudaStreamNonBlocking));
-        NRCHPM_CUDA(cudaStreamCreateWithFlags(&train_stream_, cudaStreamNonBlocking));
+        // training gets the higher priority: its (small) kernels slot in as soon as their records have landed -- i.e. while the first
+        // inference chunk is still crossing PCIe -- instead of queueing behind the persistent inference launches
+        int prio_lo = 0, prio_hi = 0;
+        NRCHPM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        NRCHPM_CUDA(cudaStreamCreateWithPriority(&train_stream_, cudaStreamNonBlocking, prio_hi));
     }
     while (pipe_events_.size() < 2 * (size_t)n_chunks + 5) {
         cudaEvent_t e; NRCHPM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));

@@ -17,7 +17,8 @@ pytestmark = pytest.mark.gpu
 FR = np.array([0.3183, 0.7071, 0.1234, 0.9876], np.float32)
 
 
-def setup(scene_id, W, H, oracle, *, train_pixels=1024, ring_frac=1.0, prl=1, prob=0.0, spp=1, trl=1, env=(0, 0, 0), compact=True, nrc=None, blend=False):
+def setup(scene_id, W, H, oracle, *, train_pixels=1024, ring_frac=1.0, prl=1, prob=0.0, spp=1, trl=1, env=(0, 0, 0), compact=True, nrc=None, blend=False,
+          log2_infer_batch=None):
     from nrc_hpm_renderer_b200 import AppConfig, Camera, HpmSceneConfig
     from nrc_hpm_renderer_b200.renderer import HpmScene, NrcHpmRenderer, make_render_config
     grid = np.ascontiguousarray(golden("wdas_cloud_sixteenth_u8.npz")["data"])
@@ -25,6 +26,8 @@ def setup(scene_id, W, H, oracle, *, train_pixels=1024, ring_frac=1.0, prl=1, pr
     app.scene = HpmSceneConfig.preset(scene_id)
     app.primary_ray_length, app.primary_ray_prob, app.train_spp, app.train_ring_buf_size = prl, prob, spp, ring_frac
     app.train_ray_length = trl
+    if log2_infer_batch is not None:
+        app.log2_infer_batch_size = log2_infer_batch          # the renderer's filter granularity == the cache's batch size (one AppConfig)
     cam = Camera(aspect=W / H)
     scene = HpmScene(grid, app.scene, env_color=env)
     cfg = make_render_config(W, H, app, blend=blend, compact_inference=compact, train_pixels=train_pixels, parity_q2=False)
@@ -156,7 +159,7 @@ def test_frame_compact_equals_reference_mode(oracle_lib):
     for compact in (True, False):
         app = AppConfig.default(); app.log2_train_batch_size, app.train_batch_count, app.log2_infer_batch_size = 9, 2, 12
         nrc = N.NeuralRadianceCache(app)
-        r, *_ = setup(0, W, H, oracle_lib, train_pixels=1024, compact=compact, nrc=nrc)
+        r, *_ = setup(0, W, H, oracle_lib, train_pixels=1024, compact=compact, nrc=nrc, log2_infer_batch=12)
         frames = []
         for f in range(3):
             r.Render(True, FR + np.float32(0.05 * f))
@@ -181,5 +184,8 @@ def test_frame_compact_equals_reference_mode(oracle_lib):
     assert np.array_equal(a, b, equal_nan=True)
     prim = renderers[0].read(R.BUF_PRIMARY_COLOR).reshape(H, W, 4)
     assert np.any(a[..., :3] != prim[..., :3])                                    # the cache term is really there
+    # a renderer whose filter granularity differs from the cache's batch size would silently skip batches: refused
+    with pytest.raises(Exception, match="infer_batch_size"):
+        setup(0, W, H, oracle_lib, train_pixels=1024, compact=False, nrc=caches[1], log2_infer_batch=13)
     # frame 0: NRC output is exactly zero -> image == primary estimate; later frames add a non-negative cache term
     assert np.any(imgs[0][2] != imgs[0][0])
