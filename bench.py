@@ -203,10 +203,12 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the hot path is sm_100a code with no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from nrc_hpm_renderer_b200 import AppConfig, _lib
     from nrc_hpm_renderer_b200.nrc import NeuralRadianceCache
-    from nrc_hpm_renderer_b200.parallel import GradientAllReduce
+    from nrc_hpm_renderer_b200.parallel import GradientAllReduce, OverlappedInferAndTrain, PeerGradientExchange, make_gradient_exchange
 
     app = AppConfig.default()                          # reference default argv: hash grid + OneBlob, 64 x 6, lr 0.01, EMA 0.99
     nrc = NeuralRadianceCache(app)
@@ -220,10 +222,24 @@ def run_ours(args):
     h_tgt = [(rng.random((n_train, 3), dtype=np.float32) * 2).astype(np.float32) for _ in range(N_SETS)]
     d_tin = [torch.from_numpy(a).cuda() for a in h_tin]
     d_tgt = [torch.from_numpy(a).cuda() for a in h_tgt]
-    allreduce = GradientAllReduce(nrc, world) if world > 1 else None
+    overlap_default = 1 if (world > 1 and os.environ.get("NRCHPM_EXCHANGE", "peer") == "nccl") else 0
+    # N > 1: the tile's inference runs underneath the gradient all-reduces (parallel.OverlappedInferAndTrain); N = 1 keeps the
+    # reference's serial Inference() -> Train() schedule unless --overlap asks for the same two-stream schedule
+    overlap = args.overlap if args.overlap is not None else overlap_default
+    runner = OverlappedInferAndTrain(nrc, world) if overlap else None
+    allreduce = make_gradient_exchange(nrc, world) if (world > 1 and runner is None) else None
+
+    def exchange_gradients():
+        if isinstance(allreduce, PeerGradientExchange):
+            allreduce.run(sp)
+        else:
+            allreduce.run()
 
     def step(i):
         s = i % N_SETS
+        if runner is not None:
+            runner.run(d_in[s], d_out[s], N_INFER, d_tin[s], d_tgt[s], TRAIN_BATCH, TRAIN_BATCHES)
+            return
         nrc.inference(d_in[s], d_out[s], N_INFER, True, sp)                      # Inference(): one batch (2^21 >= W*H), EMA weights
         for b in range(TRAIN_BATCHES):                                           # Train(): 4 x training_step
             tin = d_tin[s][b * TRAIN_BATCH:(b + 1) * TRAIN_BATCH]; tgt = d_tgt[s][b * TRAIN_BATCH:(b + 1) * TRAIN_BATCH]
@@ -231,7 +247,7 @@ def run_ours(args):
                 nrc.training_step(tin, tgt, TRAIN_BATCH, True, sp)
             else:
                 nrc.training_step(tin, tgt, TRAIN_BATCH, False, sp)
-                allreduce.run()
+                exchange_gradients()
                 nrc.optimizer_step(sp)
 
     def barrier():
@@ -252,6 +268,9 @@ def run_ours(args):
     e0.record(stream)
     for i in range(args.steps):
         s = (warmup + i) % N_SETS
+        if runner is not None:
+            step(warmup + i)
+            continue
         # dominant kernel, timed live on its own stream: the fused encode + MLP inference launch
         ev_k[i][0].record(stream)
         nrc.inference(d_in[s], d_out[s], N_INFER, True, sp)
@@ -262,14 +281,49 @@ def run_ours(args):
                 nrc.training_step(tin, tgt, TRAIN_BATCH, True, sp)
             else:
                 nrc.training_step(tin, tgt, TRAIN_BATCH, False, sp)
-                allreduce.run()
+                exchange_gradients()
                 nrc.optimizer_step(sp)
     e1.record(stream)
     barrier()
     launches = _lib.lib().nrchpm_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
+    if runner is not None:
+        # the overlapped schedule has no serial inference launch to bracket: time the dominant kernel alone afterwards
+        for i in range(args.steps):
+            s = (warmup + i) % N_SETS
+            ev_k[i][0].record(stream)
+            nrc.inference(d_in[s], d_out[s], N_INFER, True, sp)
+            ev_k[i][1].record(stream)
+        torch.cuda.synchronize()
     ms_kernel = float(np.mean([a.elapsed_time(b) for a, b in ev_k]))
+    # exposed cost of the gradient exchange: the same schedule with the all-reduce left out (replicas diverge; timing only)
+    exchange = None
+    if world > 1:
+        saved = runner.allreduce if runner is not None else None
+        if runner is not None:
+            runner.allreduce = None
+        barrier()
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_x = max(3, min(args.steps, 50))
+        x0.record(stream)
+        for i in range(n_x):
+            if runner is not None:
+                step(i)
+            else:
+                s = i % N_SETS
+                nrc.inference(d_in[s], d_out[s], N_INFER, True, sp)
+                for b in range(TRAIN_BATCHES):
+                    nrc.training_step(d_tin[s][b * TRAIN_BATCH:(b + 1) * TRAIN_BATCH], d_tgt[s][b * TRAIN_BATCH:(b + 1) * TRAIN_BATCH], TRAIN_BATCH, True, sp)
+        x1.record(stream)
+        barrier()
+        ms_nocomm = x0.elapsed_time(x1) / n_x
+        if runner is not None:
+            runner.allreduce = saved
+        ar = runner.allreduce if runner is not None else allreduce
+        exchange = {"kind": "own kernel over peer memory (nrc_peer_reduce_kernel: P2P loads/stores over NVLink)" if isinstance(ar, PeerGradientExchange) else "NCCL all-reduce",
+                    "bytes_per_training_step": ar.bytes_per_step, "all_reduces_per_step": TRAIN_BATCHES, "ms_per_step_without_exchange": ms_nocomm,
+                    "schedule": "inference chunks overlap the all-reduces" if runner is not None else "serial"}
     if world > 1:
         t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
     ms_step = ms / args.steps
@@ -320,6 +374,10 @@ def run_ours(args):
                             "peak_source": pk["which"], "ms_per_launch": ms_kernel, "algorithmic_bytes_per_query": BYTES_PER_QUERY,
                             "tensor": {"achieved_tflops": achieved_tf, "peak_tflops": pk["tflops_sustained"], "frac": achieved_tf / pk["tflops_sustained"], "flop_per_query": FLOP_PER_QUERY_H6}},
                "loss": nrc.GetLoss()}
+        out["config"]["schedule"] = "inference overlapped with training (snapshot of the pre-training parameters)" if runner is not None else "Inference() then Train(), serial (reference order)"
+        if exchange is not None:
+            exchange["exposed_ms_per_step"] = ms_step - exchange["ms_per_step_without_exchange"]
+            out["gradient_exchange"] = exchange
         if world == 1:
             try:
                 out["cpu_baseline"] = cpu_baseline_leg()
@@ -342,6 +400,7 @@ def main():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--overlap", type=int, default=None, help="1: two-stream schedule (inference chunks under the optimizer / all-reduce); default: only for N > 1")
     ap.add_argument("--no-frame", action="store_true", help="skip the full-frame leg (tracking + NRC + compositing)")
     args = ap.parse_args()
     return run_reference(args) if args.impl == "reference" else run_ours(args)

@@ -85,11 +85,29 @@ int nrc_set_ema(nrc_cache* c, const float* host_ema);
  * nrc_optimizer_step. */
 int nrc_gradient_buffers(nrc_cache* c, float** d_mlp_grad_f32, void** d_enc_grad_f16);
 
+/* Data-parallel training without a library collective: the gradients of nrc_training_step(run_optimizer=0) are summed
+ * across the ranks of ONE node by a kernel of this library that loads and stores peer HBM over NVLink (buffers shared with
+ * cudaIpc).  nrc_peer_export fills NRC_PEER_HANDLE_BYTES bytes for this rank; the caller gathers them from every rank (any
+ * transport; rank-major) and passes all of them to nrc_peer_setup; nrc_peer_exchange then replaces the all-reduce of
+ * nrc_gradient_buffers: afterwards nrc_optimizer_step applies the MEAN gradient.  Every rank must call it once per step. */
+#define NRC_PEER_HANDLE_BYTES 192
+int nrc_peer_export(nrc_cache* c, uint8_t* handles_out);
+int nrc_peer_setup(nrc_cache* c, int rank, int world, const uint8_t* all_handles);
+int nrc_peer_exchange(nrc_cache* c, void* stream);
+
 /* Encoding only: d_in float[n][5] -> d_out __half[n][input_width] (row per record). */
 int nrc_encode_batch(nrc_cache* c, const float* d_in, uint32_t n, int use_ema, void* d_out_half, void* stream);
 /* Network::inference on n records (any n > 0; tcnn requires a multiple of 256, object.h:150). use_ema=1 is what the
  * reference's Inference() does. */
 int nrc_inference_batch(nrc_cache* c, const float* d_in, float* d_out, uint32_t n, int use_ema, void* stream);
+/* use_ema = 2 in nrc_inference_batch / nrc_inference_indexed evaluates the parameters captured by the last
+ * nrc_snapshot_params (a device-to-device copy of the EMA or the working weights, stream-ordered on `stream`).  A caller that
+ * overlaps Inference() with Train() -- e.g. to hide the gradient all-reduce of a multi-GPU training step -- snapshots first,
+ * so that the cache is still evaluated with the parameters of the previous frame (src/NeuralRadianceCache.cu:97-156 order). */
+int nrc_snapshot_params(nrc_cache* c, int use_ema, void* stream);
+/* Caps the persistent grid of the following inference launches (0 = no cap: two CTAs per SM).  With one CTA per SM a
+ * co-running kernel -- the NCCL all-reduce of a data-parallel training step -- finds registers and shared memory on every SM. */
+int nrc_set_inference_cta_limit(nrc_cache* c, uint32_t max_ctas);
 /* Compacted inference: only records d_indices[0 .. *d_count) are evaluated (read from d_in[idx], written to
  * d_out[idx]); d_count is a DEVICE counter so no host sync is needed.  max_n bounds the launch. */
 int nrc_inference_indexed(nrc_cache* c, const float* d_in, float* d_out, const uint32_t* d_indices,

@@ -67,6 +67,11 @@ SIGNATURES = {
     "nrc_encode_batch": (_I, [_P, _P, _U32, _I, _P, _P]),
     "nrc_inference_batch": (_I, [_P, _P, _P, _U32, _I, _P]),
     "nrc_inference_indexed": (_I, [_P, _P, _P, _P, _P, _U32, _I, _P]),
+    "nrc_snapshot_params": (_I, [_P, _I, _P]),
+    "nrc_set_inference_cta_limit": (_I, [_P, _U32]),
+    "nrc_peer_export": (_I, [_P, _P]),
+    "nrc_peer_setup": (_I, [_P, _I, _I, _P]),
+    "nrc_peer_exchange": (_I, [_P, _P]),
     "nrc_training_step": (_I, [_P, _P, _P, _U32, _I, _P]),
     "nrc_optimizer_step": (_I, [_P, _P]),
     "nrc_last_step_tensor": (_I, [_P, _I, _F]),

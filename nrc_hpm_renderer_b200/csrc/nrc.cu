@@ -324,6 +324,22 @@ size_t NrcCache::infer_smem_level_bytes() const {
     return (bytes % 16 == 0 && bytes <= 32768) ? bytes : 0;
 }
 
+// Parameter snapshot for inference that overlaps training (multi-GPU frames: the cache is evaluated while the gradient
+// all-reduce of a training step is in flight; Inference() must still see the parameters of the previous frame).
+void NrcCache::snapshot_params(bool use_ema, cudaStream_t s) {
+    infer_snapshot_.ensure(n_params_);
+    NRCHPM_CUDA(cudaMemcpyAsync(infer_snapshot_.ptr, use_ema ? ema16_.ptr : w16_.ptr, n_params_ * sizeof(__half), cudaMemcpyDeviceToDevice, s));
+    snapshot_valid_ = true;
+}
+// param_set: 0 working weights, 1 EMA weights (the reference's Inference()), 2 the last snapshot
+void NrcCache::inference_set(int param_set, const float* d_in, float* d_out, uint32_t n, const uint32_t* d_indices, const uint32_t* d_count, cudaStream_t s) {
+    if (param_set != 2) { inference(d_in, d_out, n, param_set != 0, d_indices, d_count, s); return; }
+    NRCHPM_REQUIRE(snapshot_valid_, "inference from the snapshot without nrc_snapshot_params");
+    infer_params_override_ = infer_snapshot_.ptr;
+    try { inference(d_in, d_out, n, true, d_indices, d_count, s); } catch (...) { infer_params_override_ = nullptr; throw; }
+    infer_params_override_ = nullptr;
+}
+
 void NrcCache::encode(const float* d_in, uint32_t n, bool use_ema, void* d_out_half, cudaStream_t s) {
     if (n == 0) return;
     nrc_encode_kernel<<<(n + 127) / 128, 128, 0, s>>>(enc_, use_ema ? ema16_.ptr : w16_.ptr, (uint32_t)n_mlp_, d_in, n, (__half*)d_out_half);
@@ -350,6 +366,7 @@ void NrcCache::inference(const float* d_in, float* d_out, uint32_t n, bool use_e
     const uint32_t wgs = (uint32_t)std::max(1, std::min<int>(kInferWgs, (int)((tiles + sm_count_ * kInferCtas - 1) / (sm_count_ * kInferCtas))));
     threads = wgs * 128;
     grid = std::min<uint32_t>((tiles + wgs - 1) / wgs, (uint32_t)sm_count_ * kInferCtas);
+    if (infer_max_ctas_) grid = std::min(grid, infer_max_ctas_);          // leave room for a co-running kernel (NCCL all-reduce)
     const size_t lvl_bytes = infer_smem_level_bytes();
     if (lvl_bytes) { a.smem_levels = NRC_SMEM_LEVELS; a.smem_level_entries = (uint32_t)(lvl_bytes / 4); }
     NRC_DISPATCH_INW(enc_.in_w, {
@@ -443,7 +460,9 @@ void NrcCache::optimizer_step(cudaStream_t s) {
     a.master = master_.ptr; a.w16 = w16_.ptr; a.ema16 = ema16_.ptr; a.grad16 = grad16_.ptr; a.m1 = m1_.ptr; a.m2 = m2_.ptr; a.steps = steps_.ptr;
     a.grid_state = grid_state_.ptr;
     a.partials = dw_source_ ? dw_source_ : dw_partials_.ptr; a.n_chunks = dw_source_ ? 1u : dw_chunks_;
-    a.lr = cfg_.learning_rate; a.beta1 = cfg_.beta1; a.beta2 = cfg_.beta2; a.eps = cfg_.epsilon; a.l2_reg = cfg_.l2_reg; a.loss_scale = cfg_.loss_scale;
+    a.lr = cfg_.learning_rate; a.beta1 = cfg_.beta1; a.beta2 = cfg_.beta2; a.eps = cfg_.epsilon; a.l2_reg = cfg_.l2_reg;
+    a.loss_scale = cfg_.loss_scale * grad_scale_;          // peer_exchange leaves the SUM over the ranks in the buffers: divide here
+    grad_scale_ = 1.0f;
     a.ema_decay = cfg_.ema_decay;
     a.log2_beta1 = std::log2(cfg_.beta1); a.log2_beta2 = std::log2(cfg_.beta2);
     a.ema_debias_old = 1 - (float)std::pow(cfg_.ema_decay, current_step_ - 1);          // ema.h:105-108
@@ -576,10 +595,25 @@ int nrc_encode_batch(nrc_cache* c, const float* d_in, uint32_t n, int use_ema, v
     return guard([&] { NRCHPM_REQUIRE(c && d_in && d_out, "null argument"); c->impl.encode(d_in, n, use_ema != 0, d_out, (cudaStream_t)stream); });
 }
 int nrc_inference_batch(nrc_cache* c, const float* d_in, float* d_out, uint32_t n, int use_ema, void* stream) {
-    return guard([&] { NRCHPM_REQUIRE(c && d_in && d_out, "null argument"); c->impl.inference(d_in, d_out, n, use_ema != 0, nullptr, nullptr, (cudaStream_t)stream); });
+    return guard([&] { NRCHPM_REQUIRE(c && d_in && d_out, "null argument"); c->impl.inference_set(use_ema, d_in, d_out, n, nullptr, nullptr, (cudaStream_t)stream); });
 }
 int nrc_inference_indexed(nrc_cache* c, const float* d_in, float* d_out, const uint32_t* idx, const uint32_t* cnt, uint32_t max_n, int use_ema, void* stream) {
-    return guard([&] { NRCHPM_REQUIRE(c && d_in && d_out && idx, "null argument"); c->impl.inference(d_in, d_out, max_n, use_ema != 0, idx, cnt, (cudaStream_t)stream); });
+    return guard([&] { NRCHPM_REQUIRE(c && d_in && d_out && idx, "null argument"); c->impl.inference_set(use_ema, d_in, d_out, max_n, idx, cnt, (cudaStream_t)stream); });
+}
+int nrc_peer_export(nrc_cache* c, uint8_t* handles_out) {
+    return guard([&] { NRCHPM_REQUIRE(c && handles_out, "null argument"); c->impl.peer_export(handles_out); });
+}
+int nrc_peer_setup(nrc_cache* c, int rank, int world, const uint8_t* all_handles) {
+    return guard([&] { NRCHPM_REQUIRE(c && all_handles, "null argument"); c->impl.peer_setup(rank, world, all_handles); });
+}
+int nrc_peer_exchange(nrc_cache* c, void* stream) {
+    return guard([&] { NRCHPM_REQUIRE(c, "null cache"); c->impl.set_stream_for_loss((cudaStream_t)stream); c->impl.peer_exchange((cudaStream_t)stream); });
+}
+int nrc_set_inference_cta_limit(nrc_cache* c, uint32_t max_ctas) {
+    return guard([&] { NRCHPM_REQUIRE(c, "null cache"); c->impl.set_inference_cta_limit(max_ctas); });
+}
+int nrc_snapshot_params(nrc_cache* c, int use_ema, void* stream) {
+    return guard([&] { NRCHPM_REQUIRE(c, "null cache"); c->impl.snapshot_params(use_ema != 0, (cudaStream_t)stream); });
 }
 int nrc_training_step(nrc_cache* c, const float* d_in, const float* d_tgt, uint32_t batch, int run_opt, void* stream) {
     return guard([&] { NRCHPM_REQUIRE(c && d_in && d_tgt, "null argument"); c->impl.set_stream_for_loss((cudaStream_t)stream); c->impl.training_step(d_in, d_tgt, batch, run_opt != 0, (cudaStream_t)stream); });
@@ -617,6 +651,55 @@ void NrcCache::gradient_buffers(float** mlp, void** enc) {
     if (mlp) *mlp = mlp_grad_f32_.ptr;
     if (enc) *enc = n_grid_ ? (void*)(grad16_.ptr + n_mlp_) : nullptr;
 }
+// ---- gradient exchange over peer memory (kernel: nrc_peer_reduce_kernel)
+void NrcCache::peer_export(uint8_t* out) {
+    NRCHPM_REQUIRE(n_grid_ % 8 == 0, "peer exchange needs the encoding gradient to be a multiple of 16 bytes");
+    mlp_grad_f32_.ensure(n_mlp_); mlp_sum_.ensure(n_mlp_);
+    if (!peer_flag_words_.ptr) { peer_flag_words_.allocate(2 * kMaxPeers); peer_flag_words_.zero(); peer_done_.allocate(1); peer_done_.zero(); }
+    NRCHPM_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h[3];
+    NRCHPM_CUDA(cudaIpcGetMemHandle(&h[0], grad16_.ptr));
+    NRCHPM_CUDA(cudaIpcGetMemHandle(&h[1], mlp_grad_f32_.ptr));
+    NRCHPM_CUDA(cudaIpcGetMemHandle(&h[2], peer_flag_words_.ptr));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    std::memcpy(out, h, sizeof(h));
+}
+void NrcCache::peer_setup(int rank, int world, const uint8_t* handles) {
+    NRCHPM_REQUIRE(world >= 2 && world <= kMaxPeers && rank >= 0 && rank < world, "peer exchange: 2..8 ranks");
+    NRCHPM_REQUIRE(peer_flag_words_.ptr, "peer_setup before peer_export");
+    for (int p = 0; p < world; p++) {
+        if (p == rank) { peer_grad_[p] = grad16_.ptr; peer_mlp_[p] = mlp_grad_f32_.ptr; peer_flags_[p] = peer_flag_words_.ptr; continue; }
+        cudaIpcMemHandle_t h[3];
+        std::memcpy(h, handles + (size_t)p * kPeerHandleBytes, sizeof(h));
+        NRCHPM_CUDA(cudaIpcOpenMemHandle(&peer_grad_[p], h[0], cudaIpcMemLazyEnablePeerAccess));
+        NRCHPM_CUDA(cudaIpcOpenMemHandle(&peer_mlp_[p], h[1], cudaIpcMemLazyEnablePeerAccess));
+        NRCHPM_CUDA(cudaIpcOpenMemHandle(&peer_flags_[p], h[2], cudaIpcMemLazyEnablePeerAccess));
+    }
+    peer_rank_ = rank; peer_world_ = world;
+}
+void NrcCache::peer_exchange(cudaStream_t s) {
+    NRCHPM_REQUIRE(peer_world_ >= 2, "nrc_peer_exchange before nrc_peer_setup");
+    NRCHPM_REQUIRE(grads_pending_ && !dw_source_, "nrc_peer_exchange: call nrc_training_step(run_optimizer=0) first");
+    nrc_reduce_partials_kernel<<<(unsigned)((n_mlp_ + 255) / 256), 256, 0, s>>>(dw_partials_.ptr, dw_chunks_, (uint32_t)n_mlp_, mlp_grad_f32_.ptr);
+    check_launch("nrc_reduce_partials_kernel");
+    PeerArgs a{};
+    a.rank = peer_rank_; a.world = peer_world_; a.token = ++peer_token_;
+    for (int p = 0; p < peer_world_; p++) {
+        a.grad[p] = reinterpret_cast<int4*>(reinterpret_cast<__half*>(peer_grad_[p]) + n_mlp_);
+        a.mlp[p] = reinterpret_cast<const float*>(peer_mlp_[p]);
+        a.flags[p] = reinterpret_cast<uint32_t*>(peer_flags_[p]);
+    }
+    a.mlp_sum = mlp_sum_.ptr; a.n_vec = n_grid_ / 8; a.n_mlp = (uint32_t)n_mlp_; a.done_counter = peer_done_.ptr;
+    if (peer_world_ <= 2) nrc_peer_reduce_kernel<2><<<sm_count_ * 2, 256, 0, s>>>(a);
+    else if (peer_world_ <= 4) nrc_peer_reduce_kernel<4><<<sm_count_ * 2, 256, 0, s>>>(a);
+    else nrc_peer_reduce_kernel<8><<<sm_count_ * 2, 256, 0, s>>>(a);
+    check_launch("nrc_peer_reduce_kernel");
+    nrc_peer_wait_kernel<<<1, 32, 0, s>>>(peer_flag_words_.ptr, peer_world_, a.token);
+    check_launch("nrc_peer_wait_kernel");
+    dw_source_ = mlp_sum_.ptr;
+    grad_scale_ = (float)peer_world_;
+}
+
 // Host-buffer inference: the records are cut into chunks of whole persistent-grid rounds and pipelined over three streams
 // (H2D copy, compute, D2H copy), so PCIe transfers of chunk i+1 / i-1 overlap the kernel of chunk i.
 void NrcCache::ensure_pipeline(uint32_t n_chunks) {

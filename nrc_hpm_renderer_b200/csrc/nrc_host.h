@@ -49,6 +49,9 @@ public:
 
     void encode(const float* d_in, uint32_t n, bool use_ema, void* d_out_half, cudaStream_t s);
     void inference(const float* d_in, float* d_out, uint32_t n, bool use_ema, const uint32_t* d_indices, const uint32_t* d_count, cudaStream_t s);
+    void inference_set(int param_set, const float* d_in, float* d_out, uint32_t n, const uint32_t* d_indices, const uint32_t* d_count, cudaStream_t s);
+    void snapshot_params(bool use_ema, cudaStream_t s);
+    void set_inference_cta_limit(uint32_t max_ctas) { infer_max_ctas_ = max_ctas; }
     void training_step(const float* d_in, const float* d_target, uint32_t B, bool run_optimizer, cudaStream_t s);
     void optimizer_step(cudaStream_t s);
     void inference_host(const float* h_in, float* h_out, uint32_t n, bool use_ema);
@@ -61,6 +64,11 @@ public:
     void set_params_fp32(const float* host_master);
     void set_ema(const float* host_ema);
     void gradient_buffers(float** mlp, void** enc);
+    // data-parallel exchange over peer memory (cudaIpc): export this rank's handles, import every rank's, exchange one step
+    static constexpr size_t kPeerHandleBytes = 3 * 64;
+    void peer_export(uint8_t* out);
+    void peer_setup(int rank, int world, const uint8_t* handles);
+    void peer_exchange(cudaStream_t s);
     void last_step_tensor(int which, float* host_out);
     void keep_dx(bool k) { keep_dx_ = k; }
     cudaStream_t stream() const { return stream_; }
@@ -100,6 +108,15 @@ private:
     cudaStream_t train_stream_ = nullptr;            // InferAndTrain on host buffers: training overlaps the inference pipeline
     DeviceBuffer<__half> infer_snapshot_;            // ... which then reads a snapshot of the pre-training parameters
     const __half* infer_params_override_ = nullptr;
+    bool snapshot_valid_ = false;
+    int peer_rank_ = -1, peer_world_ = 0;
+    uint32_t peer_token_ = 0;
+    float grad_scale_ = 1.0f;                        // ranks whose gradients were summed into the buffers (the optimizer divides)
+    void* peer_grad_[8] = {}; void* peer_mlp_[8] = {}; void* peer_flags_[8] = {};
+    DeviceBuffer<float> mlp_sum_;
+    DeviceBuffer<uint32_t> peer_flag_words_;
+    DeviceBuffer<unsigned int> peer_done_;
+    uint32_t infer_max_ctas_ = 0;                    // 0: the full persistent grid (2 CTAs per SM)
     std::vector<cudaEvent_t> pipe_events_;
 };
 

@@ -1484,4 +1484,91 @@ __global__ void __launch_bounds__(256) nrc_grid_state_gather_kernel(const GridAd
     else { dst[2 * i] = f[0]; dst[2 * i + 1] = f[1]; }
 }
 
+// ---------------------------------------------------------------------------------------------- data-parallel gradient exchange
+// One kernel per training step replaces the NCCL all-reduce of the gradients: every rank owns 1/world of the
+// hash-grid entries, reads that slice of every peer's fp16 gradient straight out of the peer's HBM over NVLink (P2P loads, buffers
+// shared with cudaIpc), sums in rank order (fp32) and stores the sum into every rank's gradient buffer (P2P stores) -- reduce-
+// scatter and all-gather in one pass, 2 * (world-1)/world * 28.5 MB on the wire per rank, and nothing at all for entries no rank
+// touched (the common case on the fine levels).  The small fp32 MLP gradient is summed redundantly by every rank, in rank order,
+// so all replicas hold bit-identical results.  Synchronisation: two flag rounds in peer-visible memory (system-scope release /
+// acquire): "my gradients are complete" before the first peer load, "my stores have landed" before the optimizer may run.
+constexpr int kMaxPeers = 8;
+struct PeerArgs {
+    int rank, world;
+    int4* grad[kMaxPeers];             // hash-grid gradient of every rank (own buffer at [rank]), 8 halfs per int4
+    const float* mlp[kMaxPeers];       // fp32 MLP gradient of every rank
+    uint32_t* flags[kMaxPeers];        // flags[q]: rank q's flag words [2][kMaxPeers]; slot [phase][p] is written by rank p
+    float* mlp_sum;                    // local: sum over the ranks
+    uint64_t n_vec;                    // int4 words of the hash-grid gradient
+    uint32_t n_mlp;
+    uint32_t token;                    // exchange counter, identical on every rank
+    unsigned int* done_counter;        // local
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+
+template <int WORLD>      // upper bound of a.world: 2, 4 or 8 (sizes the register tile of in-flight peer loads)
+__global__ void __launch_bounds__(256) nrc_peer_reduce_kernel(const __grid_constant__ PeerArgs a) {
+    // ---- round A: every rank's backward pass has finished (stream order makes that true for this rank at kernel start)
+    if (blockIdx.x == 0 && threadIdx.x < a.world) st_release_sys(a.flags[threadIdx.x] + a.rank, a.token);
+    if (threadIdx.x < a.world) while ((int32_t)(ld_acquire_sys(a.flags[a.rank] + threadIdx.x) - a.token) < 0) { }
+    __syncthreads();
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = gtid; i < a.n_mlp; i += stride) {
+        float sum = 0;
+        for (int p = 0; p < a.world; p++) sum += a.mlp[p][i];
+        a.mlp_sum[i] = sum;
+    }
+    const uint64_t per = (a.n_vec + a.world - 1) / a.world, begin = per * a.rank, end = min(begin + per, a.n_vec);
+    // four independent 16-byte words per thread and round: all peer loads of a round are in flight together (a remote load costs
+    // ~1 us of NVLink latency; 75 776 threads x 4 x 16 B = 4.8 MB in flight per peer keeps the links busy; 8 / WORLD words per peer so that the tile stays at 32 registers)
+    constexpr int kU = 8 / WORLD;
+    for (uint64_t i0 = begin + gtid; i0 < end; i0 += stride * kU) {
+        int4 v[WORLD][kU];
+#pragma unroll
+        for (int u = 0; u < kU; u++) {
+            const uint64_t i = i0 + (uint64_t)u * stride;
+#pragma unroll
+            for (int p = 0; p < WORLD; p++)
+                if (p < a.world) v[p][u] = i < end ? a.grad[p][i] : make_int4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < kU; u++) {
+            const uint64_t i = i0 + (uint64_t)u * stride;
+            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            uint32_t any = 0;
+#pragma unroll
+            for (int p = 0; p < WORLD; p++) {
+                if (p >= a.world) break;
+                any |= (uint32_t)(v[p][u].x | v[p][u].y | v[p][u].z | v[p][u].w);
+                const __half2* h = reinterpret_cast<const __half2*>(&v[p][u]);
+#pragma unroll
+                for (int k = 0; k < 4; k++) { const float2 f = __half22float2(h[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+            }
+            if (i >= end || (any & 0x7fff7fffu) == 0) continue;            // untouched on every rank (+-0): nothing to store anywhere
+            int4 r;
+            __half2* o = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+            for (int k = 0; k < 4; k++) o[k] = __floats2half2_rn(acc[2 * k], acc[2 * k + 1]);
+            for (int p = 0; p < a.world; p++) a.grad[p][i] = r;
+        }
+    }
+    // ---- round B: the last block of this rank tells every rank that this rank's stores are globally visible
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(a.done_counter, 1u) == gridDim.x - 1) {
+            *a.done_counter = 0;
+            __threadfence_system();
+            for (int q = 0; q < a.world; q++) st_release_sys(a.flags[q] + kMaxPeers + a.rank, a.token);
+        }
+    }
+}
+
+// the optimizer may read the summed gradients once every rank has finished storing
+__global__ void nrc_peer_wait_kernel(const uint32_t* flags, int world, uint32_t token) {
+    if ((int)threadIdx.x < world) while ((int32_t)(ld_acquire_sys(flags + kMaxPeers + threadIdx.x) - token) < 0) { }
+}
+
 }  // namespace nrchpm

@@ -13,6 +13,7 @@ from . import _lib
 from .config import AppConfig
 
 MASTER, WORKING, EMA, GRAD, ADAM_M, ADAM_V, STEPS = range(7)
+SNAPSHOT = 2          # `use_ema` value of inference(): the parameters captured by snapshot_params()
 
 
 def _fp(a: np.ndarray):
@@ -109,6 +110,27 @@ class NeuralRadianceCache:
 
     def inference(self, d_in, d_out, n, use_ema=True, stream=None):
         _lib.check(_lib.lib().nrc_inference_batch(self._h, _dptr(d_in), _dptr(d_out), n, int(use_ema), stream))
+
+    def snapshot_params(self, use_ema=True, stream=None):
+        """capture the parameters inference(..., use_ema=SNAPSHOT) evaluates (stream-ordered device-to-device copy)"""
+        _lib.check(_lib.lib().nrc_snapshot_params(self._h, int(use_ema), stream))
+
+    PEER_HANDLE_BYTES = 192
+
+    def peer_export(self) -> bytes:
+        buf = C.create_string_buffer(self.PEER_HANDLE_BYTES)
+        _lib.check(_lib.lib().nrc_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_setup(self, rank: int, world: int, all_handles: bytes):
+        assert len(all_handles) == world * self.PEER_HANDLE_BYTES
+        _lib.check(_lib.lib().nrc_peer_setup(self._h, rank, world, C.create_string_buffer(all_handles, len(all_handles))))
+
+    def peer_exchange(self, stream=None):
+        _lib.check(_lib.lib().nrc_peer_exchange(self._h, stream))
+
+    def set_inference_cta_limit(self, max_ctas: int):
+        _lib.check(_lib.lib().nrc_set_inference_cta_limit(self._h, int(max_ctas)))
 
     def inference_indexed(self, d_in, d_out, d_indices, d_count, max_n, use_ema=True, stream=None):
         _lib.check(_lib.lib().nrc_inference_indexed(self._h, _dptr(d_in), _dptr(d_out), _dptr(d_indices),
