@@ -39,6 +39,7 @@ SKY_HALF = np.array([62.317, 42.295, 76.707], np.float32) / 2
 METRIC, UNIT = "nrc_queries_per_s_1080p_infer_and_train", "queries/s"
 FLOP_PER_QUERY_H6 = 2 * (48 * 64 + 5 * 64 * 64 + 64 * 3)        # 47 488 (H = 6)
 BYTES_PER_QUERY = 20 + 12 + 16 * 8 * 4                            # record in + radiance out + hash-grid gathers = 544 B
+NCU_DRAM_BYTES_PER_LAUNCH = 70_055_168 + 11_916_032               # ncu capture of the inference launch (profiles/, round 1)
 
 
 def synth_records(rng, n):
@@ -370,7 +371,10 @@ def run_ours(args):
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps},
                "gpu_launches": int(launches), "clocks": clocks,
                "roofline": {"kernel": "nrc_forward_kernel<48,false> (fused hash-grid/OneBlob encode + 7-layer tcgen05 MLP + fp32 output)", "bound": "hbm",
-                            "achieved": achieved_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / pk["hbm_gbs"], "traffic": None,
+                            "achieved": achieved_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / pk["hbm_gbs"], "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch (profiles/r01_ncu_fwd_infer_one_level_per_round.txt): "
+                                              "the 28.5 MB hash tables are L2-resident, DRAM sees the record I/O (66.4 MB) only",
+                            "l2": {"sectors_per_query": 57.2, "l1_to_l2_request_unit_busy": 0.66, "lts_throughput": 0.49, "note": "ncu, same capture: the unit this kernel loads most is the L1->L2 request path (one 32-byte sector per request, divergent gathers)"},
                             "peak_source": pk["which"], "ms_per_launch": ms_kernel, "algorithmic_bytes_per_query": BYTES_PER_QUERY,
                             "tensor": {"achieved_tflops": achieved_tf, "peak_tflops": pk["tflops_sustained"], "frac": achieved_tf / pk["tflops_sustained"], "flop_per_query": FLOP_PER_QUERY_H6}},
                "loss": nrc.GetLoss()}

@@ -291,8 +291,19 @@ __device__ __forceinline__ __half2 level_finish(const LevelLoads& s) {
     return r;
 }
 
+// one level per round, index arithmetic specialised per KIND (no pipelining: see the measurements at NRC_GATHER_PIPE)
+template <int KIND, class Put>
+__device__ __forceinline__ void hashgrid_run_simple(const EncParams& e, const __half2* __restrict__ grid, float x0, float x1, float x2, int lb, int le, Put& put) {
+    for (int l = lb; l < le; l++) {
+        LevelLoads A;
+        level_issue<KIND>(e, grid, l, x0, x1, x2, A);
+        put.put2(2 * l, level_finish<KIND>(A));
+    }
+}
+
 template <int KIND, class Put>
 __device__ __forceinline__ void hashgrid_run(const EncParams& e, const __half2* __restrict__ grid, float x0, float x1, float x2, int lb, int le, Put& put) {
+    if (NRC_GATHER_PIPE == 2) { hashgrid_run_simple<KIND>(e, grid, x0, x1, x2, lb, le, put); return; }
     LevelLoads A, B;
     level_issue<KIND>(e, grid, lb, x0, x1, x2, A);
     for (int l = lb; l < le; l += 2) {
@@ -516,7 +527,7 @@ constexpr uint32_t kColD = 0, kColA = 96, kColsPerWg = 128;
 #define NRC_INFER_CTAS 2
 #endif
 #ifndef NRC_INFER_UNROLL
-#define NRC_INFER_UNROLL (NRC_GATHER_PIPE ? 0 : 1)
+#define NRC_INFER_UNROLL (NRC_GATHER_PIPE ? 0 : 1)      // 0 selects hashgrid_pipelined (PIPE 1: pipelined, PIPE 2: per-kind, one level per round)
 #endif
 #ifndef NRC_SMEM_LEVELS
 #define NRC_SMEM_LEVELS 0            // coarse hash-grid levels staged in shared memory by the inference kernel

@@ -89,7 +89,20 @@ def make_gradient_exchange(nrc, world: int, group=None, kind: str | None = None)
     import os
     kind = kind or os.environ.get("NRCHPM_EXCHANGE", "peer")
     if kind == "peer":
-        return PeerGradientExchange(nrc, world, group)
+        # every rank must take the same path: agree on whether the cudaIpc setup worked everywhere, else use NCCL
+        import torch
+        import torch.distributed as dist
+        ex, err = None, None
+        try:
+            ex = PeerGradientExchange(nrc, world, group)
+        except Exception as e:          # e.g. no peer access between the devices
+            err = e
+        ok = torch.tensor([1 if ex is not None else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 1:
+            return ex
+        if dist.get_rank(group) == 0:
+            print(f"[nrc_hpm_renderer_b200] peer-memory gradient exchange unavailable ({err}); using the NCCL all-reduce", file=__import__("sys").stderr)
     return GradientAllReduce(nrc, world, group)
 
 
