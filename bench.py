@@ -196,6 +196,41 @@ def frame_leg(torch, stream, steps, warmup):
     return out
 
 
+def frame_tiles_leg(torch, dist, rank, world, steps, warmup):
+    """BASELINE config 5: a 3840x2160 frame cut into `world` column strips (one per GPU), tracking + inference per strip without any
+    exchange, cache training data-parallel (1/world of every batch per rank, gradients summed through peer memory).  ms per frame =
+    max over ranks of the per-rank frame time (CUDA events)."""
+    from nrc_hpm_renderer_b200 import AppConfig, Camera, HpmSceneConfig, volume
+    from nrc_hpm_renderer_b200.nrc import NeuralRadianceCache
+    from nrc_hpm_renderer_b200.parallel import PeerGradientExchange
+    from nrc_hpm_renderer_b200.renderer import HpmScene, NrcHpmRenderer, make_tile_render_config, tile_app_config
+    Wt, Ht = 3840, 2160
+    path = os.path.join(ROOT, "data", "wdas_cloud_quarter_u8.npz")
+    if not os.path.exists(path):
+        return {"error": "bundled volume fixture missing"}
+    grid = volume.load_volume(path).data
+    app = AppConfig.default(); app.scene = HpmSceneConfig.preset(0)
+    ta = tile_app_config(app, world)
+    nrc = NeuralRadianceCache(ta)
+    PeerGradientExchange(nrc, world)                       # Train() inside Render() now exchanges after every step
+    scene = HpmScene(grid, ta.scene)
+    cfg = make_tile_render_config(Wt, Ht, ta, rank, world)
+    r = NrcHpmRenderer(Wt, Ht, False, Camera(aspect=Wt / Ht), ta, scene, nrc, render_config=cfg)
+    rng = np.random.default_rng(1337)
+    ms = []
+    for i in range(warmup + steps):
+        fr = rng.random(4).astype(np.float32)
+        dist.barrier()
+        r.Render(True, fr); r.sync()
+        if i >= warmup:
+            ms.append(r.GetFrameTimeMS())
+    t = torch.tensor([float(np.mean(ms))], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out = {"resolution": [Wt, Ht], "tiles": world, "strip_columns": [int(cfg.x_begin), int(cfg.x_end)], "train_records_per_rank_and_step": ta.train_batch_size,
+           "ms_per_frame": float(t.item()), "frames_per_s": 1e3 / float(t.item()), "loss": nrc.GetLoss()}
+    r.Destroy(); scene.Destroy(); nrc.Destroy()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -359,6 +394,12 @@ def run_ours(args):
     h2d = N_INFER * 20 + n_train * 32
     d2h = N_INFER * 12 + 4 * TRAIN_BATCHES
 
+    frame_tiles = None
+    if world > 1 and not args.no_frame:
+        try:
+            frame_tiles = frame_tiles_leg(torch, dist, rank, world, steps=max(3, min(args.steps, 30)), warmup=5)
+        except Exception as e:
+            frame_tiles = {"error": str(e)[:300]}
     if rank == 0:
         pk = peaks()
         achieved_gbs = BYTES_PER_QUERY * N_INFER / (ms_kernel * 1e-3) / 1e9
@@ -382,6 +423,8 @@ def run_ours(args):
         if exchange is not None:
             exchange["exposed_ms_per_step"] = ms_step - exchange["ms_per_step_without_exchange"]
             out["gradient_exchange"] = exchange
+        if frame_tiles is not None:
+            out["frame_4k_tiles"] = frame_tiles
         if world == 1:
             try:
                 out["cpu_baseline"] = cpu_baseline_leg()

@@ -89,7 +89,9 @@ int nrc_gradient_buffers(nrc_cache* c, float** d_mlp_grad_f32, void** d_enc_grad
  * across the ranks of ONE node by a kernel of this library that loads and stores peer HBM over NVLink (buffers shared with
  * cudaIpc).  nrc_peer_export fills NRC_PEER_HANDLE_BYTES bytes for this rank; the caller gathers them from every rank (any
  * transport; rank-major) and passes all of them to nrc_peer_setup; nrc_peer_exchange then replaces the all-reduce of
- * nrc_gradient_buffers: afterwards nrc_optimizer_step applies the MEAN gradient.  Every rank must call it once per step. */
+ * nrc_gradient_buffers: afterwards nrc_optimizer_step applies the MEAN gradient.  Every rank must call it once per step.
+ * After nrc_peer_setup, nrc_train / nrc_infer_and_train / hpm_render(train=1) exchange after every training step by themselves
+ * (all ranks must then render in lockstep). */
 #define NRC_PEER_HANDLE_BYTES 192
 int nrc_peer_export(nrc_cache* c, uint8_t* handles_out);
 int nrc_peer_setup(nrc_cache* c, int rank, int world, const uint8_t* all_handles);
@@ -175,6 +177,9 @@ typedef struct hpm_render_config {
                                   0: reference behaviour, every record of every batch whose filter flag is set */
     /* screen partition for multi-GPU runs: this renderer owns pixel columns [x_begin, x_end) */
     uint32_t x_begin, x_end;
+    /* ... and the train-pixel lattice columns [train_tx0, train_tx0 + train_width) of the frame's lattice (train pixel (tx,ty)
+     * sits at render pixel ((train_tx0+tx)*train_x_dist, ty*train_y_dist) and seeds its RNG with the frame-wide lattice column) */
+    uint32_t train_tx0;
 } hpm_render_config;
 
 /* nrc may be NULL (pass-level use / McHpmRenderer only).  stream: cudaStream_t or NULL. */

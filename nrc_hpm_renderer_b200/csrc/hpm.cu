@@ -46,7 +46,7 @@ Renderer::Renderer(Scene* scene, NrcCache* nrc, const hpm_render_config& cfg, cu
     dcfg_.train_x_dist = cfg_.train_x_dist; dcfg_.train_y_dist = cfg_.train_y_dist; dcfg_.train_spp = cfg_.train_spp;
     dcfg_.primary_ray_length = cfg_.primary_ray_length; dcfg_.primary_ray_prob = cfg_.primary_ray_prob;
     dcfg_.train_ring_size = cfg_.train_ring_size; dcfg_.train_ray_length = cfg_.train_ray_length; dcfg_.infer_batch_size = cfg_.infer_batch_size;
-    dcfg_.x_begin = cfg_.x_begin; dcfg_.x_end = cfg_.x_end;
+    dcfg_.x_begin = cfg_.x_begin; dcfg_.x_end = cfg_.x_end; dcfg_.train_tx0 = cfg_.train_tx0;
     blend_ = cfg_.blend != 0;
 
     output_.allocate(n_pixels_); primary_color_.allocate(n_pixels_); info_.allocate(n_pixels_);

@@ -521,8 +521,16 @@ void NrcCache::run_inference(const uint32_t* filter_host) {
 
 void NrcCache::run_train() {
     const uint32_t B = cfg_.train_batch_size;
-    for (uint32_t i = 0; i < cfg_.train_batch_count; i++)                        // src/NeuralRadianceCache.cu:147-156
-        training_step(train_in_ + 5 * (size_t)i * B, train_target_ + 3 * (size_t)i * B, B, true, stream_);
+    for (uint32_t i = 0; i < cfg_.train_batch_count; i++) {                      // src/NeuralRadianceCache.cu:147-156
+        if (peer_world_ >= 2) {
+            // data-parallel replica (nrc_peer_setup): every rank trains on its own tile's records and applies the mean gradient
+            training_step(train_in_ + 5 * (size_t)i * B, train_target_ + 3 * (size_t)i * B, B, false, stream_);
+            peer_exchange(stream_);
+            optimizer_step(stream_);
+        } else {
+            training_step(train_in_ + 5 * (size_t)i * B, train_target_ + 3 * (size_t)i * B, B, true, stream_);
+        }
+    }
 }
 
 void NrcCache::wait_start() {

@@ -95,6 +95,35 @@ def make_render_config(width, height, app: AppConfig, *, blend=False, show_nrc=T
     return c
 
 
+def make_tile_render_config(width, height, app: AppConfig, rank: int, world: int, **kw) -> _lib.RenderConfig:
+    """Render configuration of rank `rank` of `world` screen tiles: the frame's train-pixel lattice
+    (CalcTrainSubset over the WHOLE frame) is cut into `world` column blocks; the rank owns the pixel columns that hold its block
+    (the last rank also the remainder) and trains on its block only, i.e. on 1/world of every training batch -- `app` must be the
+    per-rank AppConfig whose train batch size is the frame's divided by `world` (tile_app_config)."""
+    t_frame = app.train_batch_count * app.train_batch_size * world
+    c = make_render_config(width, height, app, train_pixels=t_frame, **kw)
+    if c.train_width % world:
+        raise ValueError(f"train lattice width {c.train_width} is not divisible by {world} tiles")
+    tw = c.train_width // world
+    c.train_tx0 = rank * tw
+    c.x_begin = rank * tw * c.train_x_dist
+    c.x_end = width if rank == world - 1 else (rank + 1) * tw * c.train_x_dist
+    c.train_ring_size = int(app.train_ring_buf_size * float(tw * c.train_height))
+    c.train_width = tw
+    return c
+
+
+def tile_app_config(app: AppConfig, world: int) -> AppConfig:
+    """per-rank AppConfig of a tile-partitioned frame: 1/world of every training batch"""
+    import copy
+    shift = world.bit_length() - 1
+    if world < 1 or (1 << shift) != world or app.log2_train_batch_size - shift < 7:
+        raise ValueError("tile count must be a power of two that leaves training batches of >= 128 records")
+    a = copy.deepcopy(app)
+    a.log2_train_batch_size = app.log2_train_batch_size - shift
+    return a
+
+
 class NrcHpmRenderer:
     """``NrcHpmRenderer(width, height, blend, camera, appConfig, scene, nrc)``"""
 

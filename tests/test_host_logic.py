@@ -100,3 +100,29 @@ def test_column_strips():
     assert column_strips(1920, 1) == [(0, 1920)]
     s = column_strips(3840, 4)
     assert [e - b for b, e in s] == [960] * 4
+
+
+def test_tile_render_configs_partition_frame_and_train_lattice():
+    """screen tiles by column strips that follow the frame's train-pixel lattice; every rank trains on 1/world of
+    each batch.  Pure host logic (ctypes struct only)."""
+    from nrc_hpm_renderer_b200 import AppConfig
+    from nrc_hpm_renderer_b200.renderer import make_render_config, make_tile_render_config, tile_app_config
+    app = AppConfig.default()
+    W, H = 3840, 2160
+    full = make_render_config(W, H, app)
+    for world in (1, 2, 4, 8):
+        ta = tile_app_config(app, world)
+        assert ta.train_batch_size * world == app.train_batch_size and ta.train_batch_count == app.train_batch_count
+        cfgs = [make_tile_render_config(W, H, ta, r, world) for r in range(world)]
+        assert cfgs[0].x_begin == 0 and cfgs[-1].x_end == W
+        for a, b in zip(cfgs, cfgs[1:]):
+            assert a.x_end == b.x_begin                                              # strips tile the frame without gaps
+        assert sum(c.train_width for c in cfgs) == full.train_width                     # lattice columns are partitioned
+        for r, c in enumerate(cfgs):
+            assert c.train_tx0 == r * c.train_width and c.train_height == full.train_height and c.train_x_dist == full.train_x_dist
+            first, last = c.train_tx0 * c.train_x_dist, (c.train_tx0 + c.train_width - 1) * c.train_x_dist
+            assert c.x_begin <= first and last < c.x_end                             # the rank's lattice pixels lie inside its strip
+            assert c.train_width * c.train_height == ta.train_batch_size * ta.train_batch_count
+    import pytest
+    with pytest.raises(ValueError):
+        tile_app_config(app, 3)
