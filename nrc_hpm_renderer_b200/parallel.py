@@ -128,7 +128,9 @@ class OverlappedInferAndTrain:
         # for NCCL's CTAs on every SM (with two per SM the all-reduce kernel waits until the chunk has drained)
         import os
         sm = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
-        self.cta_limit = int(os.environ.get("NRCHPM_OVERLAP_CTAS", sm)) if world > 1 else 0
+        self.cta_limit = int(os.environ.get("NRCHPM_OVERLAP_CTAS", sm)) if world > 1 else int(os.environ.get("NRCHPM_OVERLAP_CTAS", 0))
+        # world == 1: nothing to hide behind; "whole" releases the tile's inference as ONE capped launch next to the training steps
+        self.whole = world == 1 and os.environ.get("NRCHPM_OVERLAP_WHOLE", "0") == "1"
         self._events = [torch.cuda.Event() for _ in range(64)]
         self._ev_i = 0
 
@@ -148,6 +150,11 @@ class OverlappedInferAndTrain:
         chunk = -(-n // max(n_batches, 1))
         chunk = -(-chunk // self.align) * self.align
         off = 0
+        if self.whole:
+            nrc.set_inference_cta_limit(self.cta_limit)
+            nrc.inference(d_in[:n], d_out[:n], n, SNAPSHOT, s_inf.cuda_stream)
+            nrc.set_inference_cta_limit(0)
+            off = n
         with torch.cuda.stream(s_tr):                                       # NCCL orders itself behind the current stream
             for b in range(n_batches):
                 nrc.training_step(d_train_in[b * batch:(b + 1) * batch], d_train_target[b * batch:(b + 1) * batch], batch, False, s_tr.cuda_stream)
