@@ -16,12 +16,13 @@ Scene::Scene(const hpm_scene_desc& d, const uint8_t* grid_host) {
     NRCHPM_REQUIRE(d.dim[0] > 0 && d.dim[1] > 0 && d.dim[2] > 0, "scene: bad grid extent");
     NRCHPM_REQUIRE(d.density_factor > 0.0f, "scene: density_factor must be > 0");
     const size_t n = (size_t)d.dim[0] * d.dim[1] * d.dim[2];
+    NRCHPM_REQUIRE(n < (1ull << 32), "scene: the density grid must have fewer than 2^32 voxels");
     grid_.allocate(n);
     NRCHPM_CUDA(cudaMemcpy(grid_.ptr, grid_host, n, cudaMemcpyHostToDevice));
     dev_.grid = grid_.ptr;
     for (int i = 0; i < 3; i++) {
         dev_.dim[i] = d.dim[i]; dev_.dimf[i] = (float)d.dim[i];
-        dev_.sky[i] = d.sky_size[i]; dev_.half_sky[i] = d.sky_size[i] / 2.0f;
+        dev_.sky[i] = d.sky_size[i]; dev_.half_sky[i] = d.sky_size[i] / 2.0f; dev_.inv_sky[i] = 1.0f / d.sky_size[i];
         dev_.dl_dir[i] = d.dir_light_dir[i]; dev_.pl_pos[i] = d.point_pos[i]; dev_.pl_color[i] = d.point_color[i]; dev_.env_color[i] = d.env_color[i];
     }
     dev_.density = d.density_factor; dev_.inv_density = 1.0f / d.density_factor; dev_.g = d.g;

@@ -90,7 +90,7 @@ struct Ctx {
     const HpmoScene* sc;
     float rng;                // randomState (random.glsl:59)
     uint64_t lookups;         // density fetches (roofline accounting)
-    V3 sky, half_sky;
+    V3 sky, half_sky, inv_sky;
     float inv_max_density;
 
     void init_random(float u, float v, const float fr[4]) {        // random.glsl:61-64
@@ -119,7 +119,8 @@ struct Ctx {
     }
     float get_density(V3 p) {                                        // volume.glsl:31-39 (+ Q9 sampler)
         lookups++;
-        V3 uvw = p / sky + V3{0.5f, 0.5f, 0.5f};
+        // p / skySize as p * (1 / skySize): what a GLSL compiler emits for a vector division, and what the CUDA path computes
+        V3 uvw = V3{p.x * inv_sky.x + 0.5f, p.y * inv_sky.y + 0.5f, p.z * inv_sky.z + 0.5f};
         float fx = std::floor(uvw.x * (float)sc->dim[0]);
         float fy = std::floor(uvw.y * (float)sc->dim[1]);
         float fz = std::floor(uvw.z * (float)sc->dim[2]);
@@ -239,6 +240,7 @@ Ctx make_ctx(const HpmoScene* sc) {
     c.sc = sc; c.rng = 0; c.lookups = 0;
     c.sky = {sc->sky_size[0], sc->sky_size[1], sc->sky_size[2]};
     c.half_sky = {sc->sky_size[0] / 2.0f, sc->sky_size[1] / 2.0f, sc->sky_size[2] / 2.0f};
+    c.inv_sky = {1.0f / sc->sky_size[0], 1.0f / sc->sky_size[1], 1.0f / sc->sky_size[2]};
     c.inv_max_density = 1.0f / sc->density_factor;
     return c;
 }
