@@ -226,6 +226,7 @@ NrcCache::NrcCache(const NrcConfig& cfg, uint64_t seed) : cfg_(cfg) {
 
 NrcCache::~NrcCache() {
     for (auto e : pipe_events_) cudaEventDestroy(e);
+    if (loss_pinned_) cudaFreeHost(loss_pinned_);
     if (copy_in_stream_) { cudaStreamDestroy(copy_in_stream_); cudaStreamDestroy(copy_out_stream_); cudaStreamDestroy(compute_stream_); cudaStreamDestroy(train_stream_); }
 }
 
@@ -773,7 +774,8 @@ void NrcCache::infer_and_train_host(const float* h_in, float* h_out, uint32_t n,
     if (n) { host_in_.ensure((size_t)n * 5); host_out_.ensure((size_t)n * 3); }
     const size_t T = (size_t)B * n_batches;
     if (train) { host_tin_.ensure(T * 5); host_tgt_.ensure(T * 3); ensure_train_scratch(B); }
-    const uint32_t chunk = (uint32_t)sm_count_ * 2 * 2 * 4 * kTile;
+    uint32_t chunk = (uint32_t)sm_count_ * 2 * 2 * 8 * kTile;          // 8 tiles per resident warpgroup: 4 chunks for a 1080p frame
+    if (const char* v = std::getenv("NRCHPM_E2E_CHUNK_TILES")) chunk = (uint32_t)sm_count_ * 2 * 2 * (uint32_t)std::max(1, std::atoi(v)) * kTile;   // experiment knob
     const uint32_t n_chunks = (n + chunk - 1) / chunk;
     ensure_pipeline(n_chunks);
     const size_t e0 = 2 * (size_t)n_chunks;
@@ -795,25 +797,30 @@ void NrcCache::infer_and_train_host(const float* h_in, float* h_out, uint32_t n,
         NRCHPM_CUDA(cudaMemcpyAsync(host_tgt_.ptr, h_tgt, T * 3 * sizeof(float), cudaMemcpyHostToDevice, copy_in_stream_));
         NRCHPM_CUDA(cudaEventRecord(ev_train, copy_in_stream_));
     }
-    try {
-        if (n) queue_inference_pipeline(h_in, h_out, n, use_ema, chunk, n_chunks);
-    } catch (...) { infer_params_override_ = nullptr; throw; }
-    infer_params_override_ = nullptr;
+    // Training goes FIRST on the device: its records are small and have landed long before the first inference chunk has crossed
+    // PCIe, and the persistent inference launches cannot share an SM with the training kernels (TMEM and registers), so interleaving
+    // the two only makes every training kernel wait for a whole chunk to drain (measured: 1.81 ms; training first: see profiles/).
+    // The inference kernels wait for the last optimizer step; their H2D copies do not.  Inference still evaluates the snapshot.
     if (train) {
         NRCHPM_CUDA(cudaStreamWaitEvent(ts, ev_train, 0));
         for (uint32_t b = 0; b < n_batches; b++)
             training_step(host_tin_.ptr + (size_t)b * B * 5, host_tgt_.ptr + (size_t)b * B * 3, B, true, ts);
-        NRCHPM_CUDA(cudaMemcpyAsync(&loss_host_, loss_dev_.ptr, sizeof(float), cudaMemcpyDeviceToHost, ts));
+        if (!loss_pinned_) NRCHPM_CUDA(cudaMallocHost((void**)&loss_pinned_, sizeof(float)));   // pageable memory would make this copy block the host
+        NRCHPM_CUDA(cudaMemcpyAsync(loss_pinned_, loss_dev_.ptr, sizeof(float), cudaMemcpyDeviceToHost, ts));
         if (overlap) {
             NRCHPM_CUDA(cudaEventRecord(ev_trained, train_stream_));
             NRCHPM_CUDA(cudaStreamWaitEvent(compute_stream_, ev_trained, 0));
         }
     }
+    try {
+        if (n) queue_inference_pipeline(h_in, h_out, n, use_ema, chunk, n_chunks);
+    } catch (...) { infer_params_override_ = nullptr; throw; }
+    infer_params_override_ = nullptr;
     // later work on the cache's own stream is ordered behind this call
     NRCHPM_CUDA(cudaEventRecord(ev_done, compute_stream_));
     NRCHPM_CUDA(cudaStreamWaitEvent(stream_, ev_done, 0));
     NRCHPM_CUDA(cudaStreamSynchronize(compute_stream_));
     NRCHPM_CUDA(cudaStreamSynchronize(copy_out_stream_));
-    if (train) { loss_valid_ = true; if (loss_out) *loss_out = loss_host_; }
+    if (train) { loss_host_ = *loss_pinned_; loss_valid_ = true; if (loss_out) *loss_out = loss_host_; }
 }
 }  // namespace nrchpm

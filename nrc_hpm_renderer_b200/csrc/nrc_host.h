@@ -98,6 +98,7 @@ private:
     const float* dw_source_ = nullptr;
     bool grid_grad_dirty_ = false, grads_pending_ = false, keep_dx_ = true, loss_valid_ = true, initialised_ = false;
     float loss_host_ = 0;
+    float* loss_pinned_ = nullptr;                   // pinned landing word of the loss for the host pipeline
     // en::NeuralRadianceCache::Init state
     uint32_t infer_count_ = 0;
     float *infer_in_ = nullptr, *infer_out_ = nullptr, *train_in_ = nullptr, *train_target_ = nullptr;
