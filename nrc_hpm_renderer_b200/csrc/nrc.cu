@@ -439,7 +439,9 @@ void NrcCache::training_step(const float* d_in, const float* d_target, uint32_t 
     {
         DwArgs a{};
         a.n_hidden = H; a.n = B; a.n_mlp = (uint32_t)n_mlp_;
-        const uint32_t tiles_per_chunk = (tiles + kMaxDwChunks - 1) / kMaxDwChunks;
+        // enough chunks to fill the GPU for large batches (grid = chunks x (H + 1) CTAs), 32 for the reference's batch sizes
+        const uint32_t want_chunks = tiles <= 1024 ? 32u : std::min<uint32_t>(kMaxDwChunks, tiles / 32);
+        const uint32_t tiles_per_chunk = (tiles + want_chunks - 1) / want_chunks;
         a.kc = tiles_per_chunk * kTile;
         dw_chunks_ = (B + a.kc - 1) / a.kc;
         a.x16 = x16_.ptr; a.acts = acts_.ptr; a.dacts = dacts_.ptr; a.dout16 = dout16_.ptr; a.partials = dw_partials_.ptr;

@@ -25,7 +25,7 @@ struct NrcConfig {
     static NrcConfig from_json(const std::string& text);
 };
 
-constexpr uint32_t kMaxDwChunks = 32;
+constexpr uint32_t kMaxDwChunks = 256;      // weight-gradient partials: 32 batch chunks up to 1024 tiles (the reference's 2^14 batches), up to 256 beyond
 
 class NrcCache {
 public:
