@@ -131,6 +131,9 @@ class OverlappedInferAndTrain:
         self.cta_limit = int(os.environ.get("NRCHPM_OVERLAP_CTAS", sm)) if world > 1 else int(os.environ.get("NRCHPM_OVERLAP_CTAS", 0))
         # world == 1: nothing to hide behind; "whole" releases the tile's inference as ONE capped launch next to the training steps
         self.whole = world == 1 and os.environ.get("NRCHPM_OVERLAP_WHOLE", "0") == "1"
+        # share of the tile's records that rides along with the exchanges (capped, slower launches); the rest is evaluated up
+        # front at full occupancy.  Sized so that a capped chunk takes about as long as one exchange + optimizer window.
+        self.window_fraction = float(os.environ.get("NRCHPM_OVERLAP_FRACTION", "0.6" if world > 1 else "1.0"))
         self._events = [torch.cuda.Event() for _ in range(64)]
         self._ev_i = 0
 
@@ -147,9 +150,15 @@ class OverlappedInferAndTrain:
         s_inf.wait_stream(cur); s_tr.wait_stream(cur)
         nrc.snapshot_params(True, s_inf.cuda_stream)
         e = self._event(); e.record(s_inf); s_tr.wait_event(e)            # training overwrites what the snapshot copy reads
-        chunk = -(-n // max(n_batches, 1))
-        chunk = -(-chunk // self.align) * self.align
         off = 0
+        if self.window_fraction < 1.0 and not self.whole and n_batches > 0:
+            head = int(n * (1.0 - self.window_fraction)) // self.align * self.align
+            if head > 0:                                                    # full-occupancy launch first; training starts behind it
+                nrc.inference(d_in[:head], d_out[:head], head, SNAPSHOT, s_inf.cuda_stream)
+                e = self._event(); e.record(s_inf); s_tr.wait_event(e)
+                off = head
+        chunk = -(-(n - off) // max(n_batches, 1))
+        chunk = -(-chunk // self.align) * self.align
         if self.whole:
             nrc.set_inference_cta_limit(self.cta_limit)
             nrc.inference(d_in[:n], d_out[:n], n, SNAPSHOT, s_inf.cuda_stream)
