@@ -470,8 +470,13 @@ void NrcCache::optimizer_step(cudaStream_t s) {
     a.log2_beta1 = std::log2(cfg_.beta1); a.log2_beta2 = std::log2(cfg_.beta2);
     a.ema_debias_old = 1 - (float)std::pow(cfg_.ema_decay, current_step_ - 1);          // ema.h:105-108
     a.ema_debias_new = 1.0f / (1 - (float)std::pow(cfg_.ema_decay, current_step_));
-    nrc_optimizer_kernel<<<(unsigned)((n_params_ / 8 + 255) / 256), 256, 0, s>>>(a);
-    check_launch("nrc_optimizer_kernel");
+    NRCHPM_REQUIRE(n_mlp_ % 256 == 0, "optimizer: the network parameter count must be a multiple of 256");
+    nrc_optimizer_kernel<true><<<(unsigned)((n_mlp_ + 2047) / 2048), 256, 0, s>>>(a);
+    check_launch("nrc_optimizer_kernel<mlp>");
+    if (n_params_ > n_mlp_) {
+        nrc_optimizer_kernel<false><<<(unsigned)(((n_params_ - n_mlp_) / 8 + 255) / 256), 256, 0, s>>>(a);
+        check_launch("nrc_optimizer_kernel<encoding>");
+    }
     grid_grad_dirty_ = false;       // the optimizer re-zeroes every encoding gradient it consumed
     grads_pending_ = false;
 }

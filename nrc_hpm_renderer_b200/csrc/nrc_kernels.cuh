@@ -1381,16 +1381,27 @@ __device__ __forceinline__ float adam_update(const OptArgs& a, float wfp, float&
 // ranks into a shared list) and then runs Adam densely, one touched ENTRY (two features, one 32-byte state sector) per lane,
 // instead of executing mostly-predicated-off copies of the update.  The new fp16 weights travel back to their owner thread
 // through shared memory, so weights, EMA and the re-zeroed gradient are written with full 128-bit stores.
-__global__ void __launch_bounds__(256) nrc_optimizer_kernel(const __grid_constant__ OptArgs a) {
+// Two instantiations, two launches: MLP = true covers the network weights (dense Adam, 12 CTAs), MLP = false the hash-grid entries.
+// The encoding instance is latency-bound on its dependent loads (gradient -> ballot -> per-entry state): ncu showed 43 % of DRAM
+// peak at 3 CTAs/SM with the combined 77-register kernel; without the network branch it fits 6 CTAs/SM (measured: the training
+// step 155 -> 145 us).
+#ifndef NRC_OPT_MIN_BLOCKS
+#define NRC_OPT_MIN_BLOCKS 6
+#endif
+template <bool MLP>
+__global__ void __launch_bounds__(256, MLP ? 1 : NRC_OPT_MIN_BLOCKS) nrc_optimizer_kernel(const __grid_constant__ OptArgs a) {
     __shared__ uint32_t s_g[8][128];       // per warp: compacted gradients (half2 bits) of the touched entries ...
     __shared__ uint16_t s_el[8][128];      // ... and their entry index inside the warp's 128-entry span
     __shared__ uint32_t s_w[8][128];       // new fp16 weights (half2 bits) by rank
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t i0 = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 8;
-    const uint64_t warp_i0 = ((uint64_t)blockIdx.x * 256 + warp * 32) * 8;
-    if (warp_i0 >= a.n_params) return;                       // whole warp out of range
+    // n_mlp is a multiple of 1024 (64-wide layers, 16-aligned inputs): the network instance covers [0, n_mlp), the encoding
+    // instance starts at n_mlp; a warp (256 parameters) never straddles the boundary
+    const uint64_t base = MLP ? 0 : a.n_mlp;
+    const uint64_t i0 = base + ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 8;
+    const uint64_t warp_i0 = base + ((uint64_t)blockIdx.x * 256 + warp * 32) * 8;
+    if (warp_i0 >= (MLP ? a.n_mlp : a.n_params)) return;     // whole warp out of range
     const bool in_range = i0 < a.n_params;
-    const bool is_mlp = warp_i0 < a.n_mlp;                   // n_mlp is a multiple of 256: a warp never straddles the boundary
+    constexpr bool is_mlp = MLP;
     union V8 { int4 v; __half h[8]; uint32_t u[4]; };
     V8 g, w, e;
     g.v = make_int4(0, 0, 0, 0); w.v = g.v; e.v = g.v;
