@@ -230,6 +230,10 @@ int hpm_buffer_info(hpm_renderer* r, int which, void** d_ptr, size_t* bytes);
 int hpm_read_buffer(hpm_renderer* r, int which, void* host_out, size_t bytes);
 int hpm_write_buffer(hpm_renderer* r, int which, const void* host_in, size_t bytes);
 
+/* Self-test: number of RNG-reachable arguments (1 - k*2^-23, k < 2^23) on which the tracker's branch-free logf differs from the
+ * CUDA math library's logf (expected 0). */
+int hpm_selftest_logf(uint64_t* mismatches_out);
+
 /* Reference::Result (include/engine/graphics/Reference.hpp:17-29) -- what Reference::CompareNrc / CompareMc
  * (src/Reference.cpp:72-171; data/shader/ref/cmp1.comp, norm.comp, cmp2.comp) compute for a frame against a reference
  * frame, over the pixels whose reference alpha is not 0: mse = mean |cmp.rgb - ref.rgb|^2 / 3, the two image means,

@@ -96,6 +96,7 @@ SIGNATURES = {
     "hpm_buffer_info": (_I, [_P, _I, C.POINTER(_P), C.POINTER(_SZ)]),
     "hpm_read_buffer": (_I, [_P, _I, _P, _SZ]),
     "hpm_write_buffer": (_I, [_P, _I, _P, _SZ]),
+    "hpm_selftest_logf": (_I, [C.POINTER(_U64)]),
     "hpm_compare_images": (_I, [_P, _P, _U32, _U32, C.POINTER(CompareResult), _P]),
 }
 

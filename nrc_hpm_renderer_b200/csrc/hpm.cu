@@ -287,6 +287,19 @@ int hpm_read_buffer(hpm_renderer* r, int which, void* host, size_t bytes) { retu
 int hpm_write_buffer(hpm_renderer* r, int which, const void* host, size_t bytes) { return guard([&] { NRCHPM_REQUIRE(r && host, "null argument"); r->impl.write_buffer(which, host, bytes); }); }
 
 
+// test hook: the tracker's branch-free logf against the CUDA math library on every argument the RNG can produce
+int hpm_selftest_logf(uint64_t* mismatches_out) {
+    return guard([&] {
+        NRCHPM_REQUIRE(mismatches_out, "null argument");
+        DeviceBuffer<unsigned long long> d; d.allocate(1); d.zero();
+        hpm_logf_check_kernel<<<(1u << 23) / 256, 256>>>(d.ptr);
+        check_launch("hpm_logf_check_kernel");
+        unsigned long long h = 0;
+        NRCHPM_CUDA(cudaMemcpy(&h, d.ptr, sizeof(h), cudaMemcpyDeviceToHost));
+        *mismatches_out = h;
+    });
+}
+
 // Reference::CompareNrc / CompareMc (src/Reference.cpp:72-171): image statistics on the device, one host read-back of 20 bytes
 int hpm_compare_images(const float* d_ref_rgba, const float* d_cmp_rgba, uint32_t width, uint32_t height, hpm_compare_result* out, void* stream) {
     return guard([&] {

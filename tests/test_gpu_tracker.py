@@ -221,3 +221,13 @@ def test_majorant_bricks_are_the_same_estimator(scene_id, env, oracle_lib):
     assert np.sqrt((da ** 2).mean()) <= 0.06 * blk(a)[..., 0].mean()                      # block means agree to noise
     assert np.abs(blk(b)[..., 3] - blk(a)[..., 3]).max() <= 0.03
     assert lookups[1] < 0.5 * lookups[0], lookups                                         # what the mode is for
+
+
+def test_tracker_logf_is_the_library_logf_on_every_reachable_argument():
+    """The Woodcock loops call a branch-free logf (no denormal / zero / inf / NaN paths); it must equal CUDA's logf bit for bit on
+    all 2^23 arguments 1 - u the RNG can produce."""
+    import ctypes as C
+    from nrc_hpm_renderer_b200 import _lib
+    n = C.c_uint64(123)
+    _lib.check(_lib.lib().hpm_selftest_logf(C.byref(n)))
+    assert n.value == 0
