@@ -120,7 +120,8 @@ void Renderer::pass_gen_rays(const float fr[4]) {
     a.primary_color = primary_color_.ptr; a.info = info_.ptr; a.origin = origin_.ptr; a.dir = dir_.ptr;
     a.infer_in = infer_in_.ptr; a.infer_filter = filter_.ptr; a.active_list = active_list_.ptr; a.active_count = active_count_.ptr;
     a.lookups = counters_.ptr;
-    const dim3 block(8, 16), grid((cfg_.x_end - cfg_.x_begin + 7) / 8, (cfg_.height + 15) / 16);
+    const uint32_t tw = hpmdev::kTileW, th = 128 / tw;
+    const dim3 block(tw, th), grid((cfg_.x_end - cfg_.x_begin + tw - 1) / tw, (cfg_.height + th - 1) / th);
     if (a.sc.maj) hpm_gen_rays_kernel<true><<<grid, block, 0, stream_>>>(a);
     else hpm_gen_rays_kernel<false><<<grid, block, 0, stream_>>>(a);
     check_launch("hpm_gen_rays_kernel");
@@ -192,7 +193,8 @@ void Renderer::mc_render(const float fr[4], uint32_t path_length) {
     McArgs a{};
     a.sc = scene_->dev(); a.cam = cam_; a.cfg = dcfg_; a.frame_random = make_float4(fr[0], fr[1], fr[2], fr[3]);
     a.path_length = path_length; a.blend_factor = blend_factor_; a.output = output_.ptr; a.lookups = counters_.ptr;
-    const dim3 block(8, 16), grid((cfg_.x_end - cfg_.x_begin + 7) / 8, (cfg_.height + 15) / 16);
+    const uint32_t tw = hpmdev::kTileW, th = 128 / tw;
+    const dim3 block(tw, th), grid((cfg_.x_end - cfg_.x_begin + tw - 1) / tw, (cfg_.height + th - 1) / th);
     if (a.sc.maj) hpm_mc_render_kernel<true><<<grid, block, 0, stream_>>>(a);
     else hpm_mc_render_kernel<false><<<grid, block, 0, stream_>>>(a);
     check_launch("hpm_mc_render_kernel");
