@@ -173,10 +173,12 @@ def frame_leg(torch, stream, steps, warmup):
     app = AppConfig.default()
     app.scene = HpmSceneConfig.preset(0)
     out = {"volume": vol_name, "scene": 0}
-    for mode, compact in (("compact", True), ("all_records", False)):
+    for mode, compact, pipelined in (("compact", True, False), ("all_records", False, False), ("compact_pipelined_training", True, True)):
         nrc = NeuralRadianceCache(app)
         scene = HpmScene(grid, app.scene)
-        r = NrcHpmRenderer(W, H, False, Camera(aspect=W / H), app, scene, nrc, compact_inference=compact, stream=stream)
+        # pipelined: Train(N) runs underneath the tracking passes of frame N+1 (same order of effects); per-frame time = the main
+        # stream from gen_rays to compositing, which includes waiting for the previous frame's training before Inference()
+        r = NrcHpmRenderer(W, H, False, Camera(aspect=W / H), app, scene, nrc, compact_inference=compact, pipeline_train=pipelined, stream=stream)
         rng = np.random.default_rng(1337)
         stages = []
         for i in range(warmup + steps):
@@ -187,7 +189,7 @@ def frame_leg(torch, stream, steps, warmup):
         ms = {k: float(np.mean([s[k] for s in stages])) for k in stages[0]}
         out[mode] = {"ms": {k: round(v, 4) for k, v in ms.items()}, "frames_per_s": 1e3 / ms["total"], "density_lookups_gen_rays": int(cnt[0]),
                      "density_lookups_prep_train": int(cnt[1]), "active_records": int(cnt[2]), "loss": nrc.GetLoss()}
-        if compact:
+        if compact and not pipelined:
             # tracking roofline: L lookups x 1 B + P pixels x 36 B, and the sector-granular figure L x 32 B
             L, P = int(cnt[0]), W * H
             t = ms["gen_rays"] * 1e-3

@@ -188,6 +188,11 @@ typedef struct hpm_render_config {
     /* ... and the train-pixel lattice columns [train_tx0, train_tx0 + train_width) of the frame's lattice (train pixel (tx,ty)
      * sits at render pixel ((train_tx0+tx)*train_x_dist, ty*train_y_dist) and seeds its RNG with the frame-wide lattice column) */
     uint32_t train_tx0;
+    /* 1: Train() of frame N runs on its own stream underneath the tracking passes of frame N+1 (double-buffered train
+     * records); the order of effects stays the reference's: Inference(N), Train(N), Inference(N+1).  hpm_render returns with
+     * the training in flight; hpm_sync / nrc_get_loss wait for it.  HPM_BUF_TRAIN_INPUT / _TARGET then name the record set the
+     * NEXT frame will write.  0: everything on one stream, in the reference's order. */
+    uint32_t pipeline_train;
 } hpm_render_config;
 
 /* nrc may be NULL (pass-level use / McHpmRenderer only).  stream: cudaStream_t or NULL. */

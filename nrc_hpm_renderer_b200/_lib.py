@@ -34,7 +34,7 @@ class RenderConfig(C.Structure):
                 ("primary_ray_length", C.c_uint32), ("primary_ray_prob", C.c_float), ("train_ring_size", C.c_uint32),
                 ("train_ray_length", C.c_uint32), ("infer_batch_size", C.c_uint32), ("blend", C.c_uint32),
                 ("show_nrc", C.c_uint32), ("compact_inference", C.c_uint32), ("x_begin", C.c_uint32), ("x_end", C.c_uint32),
-                ("train_tx0", C.c_uint32)]
+                ("train_tx0", C.c_uint32), ("pipeline_train", C.c_uint32)]
 
 
 class CompareResult(C.Structure):

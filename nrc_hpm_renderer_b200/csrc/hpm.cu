@@ -74,6 +74,16 @@ Renderer::Renderer(Scene* scene, NrcCache* nrc, const hpm_render_config& cfg, cu
         train_ray_.allocate((size_t)n_train_ * 6); train_flags_.allocate(n_train_);
         block_totals_.allocate(2 * (size_t)((n_train_ + 255) / 256));
         train_in_.zero(); train_target_.zero();
+        if (cfg_.pipeline_train) {
+            train_in2_.allocate((size_t)n_train_ * 5); train_target2_.allocate((size_t)n_train_ * 3);
+            train_in2_.zero(); train_target2_.zero();
+            // high priority: the small training grids must get SM slots as the (huge) tracking grid retires CTAs, not after it
+            int prio_lo = 0, prio_hi = 0;
+            NRCHPM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            NRCHPM_CUDA(cudaStreamCreateWithPriority(&train_stream_, cudaStreamNonBlocking, prio_hi));
+            NRCHPM_CUDA(cudaEventCreateWithFlags(&ev_infer_done_, cudaEventDisableTiming));
+            NRCHPM_CUDA(cudaEventCreateWithFlags(&ev_train_done_, cudaEventDisableTiming));
+        }
         // CreateNrcTrainRingBuffer (:841-881): head = tail = 0, every ray pos (0,0,0) dir (0,0,1)
         std::vector<uint32_t> ring(2 + 6 * (size_t)n_train_, 0u);
         float* rays = reinterpret_cast<float*>(ring.data() + 2);
@@ -92,6 +102,7 @@ Renderer::Renderer(Scene* scene, NrcCache* nrc, const hpm_render_config& cfg, cu
 }
 
 Renderer::~Renderer() {
+    if (train_stream_) { cudaStreamSynchronize(train_stream_); cudaStreamDestroy(train_stream_); cudaEventDestroy(ev_infer_done_); cudaEventDestroy(ev_train_done_); }
     if (filter_host_) cudaFreeHost(filter_host_);
     for (auto& e : ev_) if (e) cudaEventDestroy(e);
 }
@@ -146,7 +157,7 @@ void Renderer::pass_prep_train(const float fr[4]) {
         a.sc = scene_->dev(); a.cfg = dcfg_; a.frame_random = make_float4(fr[0], fr[1], fr[2], fr[3]);
         a.train_ray = train_ray_.ptr; a.train_flags = train_flags_.ptr; a.ring = ring_.ptr;
         a.block_totals = block_totals_.ptr; a.n_blocks = n_blocks;
-        a.train_in = train_in_.ptr; a.train_target = train_target_.ptr; a.lookups = counters_.ptr + 1;
+        a.train_in = cur_train_in(); a.train_target = cur_train_target(); a.lookups = counters_.ptr + 1;
         if (a.sc.maj) hpm_train_trace_kernel<true><<<(n_train_ + 127) / 128, 128, 0, stream_>>>(a);
         else hpm_train_trace_kernel<false><<<(n_train_ + 127) / 128, 128, 0, stream_>>>(a);
         check_launch("hpm_train_trace_kernel");
@@ -170,6 +181,9 @@ void Renderer::render(const float fr[4], bool train) {
     NRCHPM_CUDA(cudaEventRecord(ev_[1], stream_));
     pass_prep_train(fr);                                       // the reference records it unconditionally (:2036-2042)
     NRCHPM_CUDA(cudaEventRecord(ev_[2], stream_));
+    const bool pipelined = train_stream_ != nullptr;
+    // pipelined: Train() of the previous frame has been running underneath this frame's tracking; Inference() needs its result
+    if (pipelined && train_in_flight_) { NRCHPM_CUDA(cudaStreamWaitEvent(stream_, ev_train_done_, 0)); train_in_flight_ = false; }
     if (cfg_.compact_inference) {
         nrc_->inference(infer_in_.ptr, infer_out_.ptr, n_pixels_, true, active_list_.ptr, active_count_.ptr, stream_);
     } else {
@@ -180,7 +194,21 @@ void Renderer::render(const float fr[4], bool train) {
         nrc_->run_inference(filter_host_);
     }
     NRCHPM_CUDA(cudaEventRecord(ev_[3], stream_));
-    if (train && n_train_) nrc_->run_train();
+    if (train && n_train_) {
+        if (pipelined) {
+            // same order of effects as the reference (Inference() of this frame, then Train(), then the next frame's Inference()):
+            // the training steps start when the inference above has finished and run on their own stream, next to the tracking
+            // passes of the NEXT frame (ALU-bound, no TMEM: they share the SMs with the latency-bound training kernels)
+            NRCHPM_CUDA(cudaEventRecord(ev_infer_done_, stream_));
+            NRCHPM_CUDA(cudaStreamWaitEvent(train_stream_, ev_infer_done_, 0));
+            nrc_->run_train_on(cur_train_in(), cur_train_target(), train_stream_);
+            NRCHPM_CUDA(cudaEventRecord(ev_train_done_, train_stream_));
+            train_in_flight_ = true;
+            train_set_ ^= 1;                                   // the next prep_train writes the other record set
+        } else {
+            nrc_->run_train();
+        }
+    }
     NRCHPM_CUDA(cudaEventRecord(ev_[4], stream_));
     pass_composite();
     NRCHPM_CUDA(cudaEventRecord(ev_[5], stream_));
@@ -219,8 +247,8 @@ void Renderer::buffer_info(int which, void** ptr, size_t* bytes) {
         case HPM_BUF_NRC_DIR: p = dir_.ptr; b = dir_.bytes(); break;
         case HPM_BUF_INFER_INPUT: p = infer_in_.ptr; b = infer_in_.bytes(); break;
         case HPM_BUF_INFER_OUTPUT: p = infer_out_.ptr; b = infer_out_.bytes(); break;
-        case HPM_BUF_TRAIN_INPUT: p = train_in_.ptr; b = train_in_.bytes(); break;
-        case HPM_BUF_TRAIN_TARGET: p = train_target_.ptr; b = train_target_.bytes(); break;
+        case HPM_BUF_TRAIN_INPUT: p = cur_train_in(); b = train_in_.bytes(); break;          // the set written last
+        case HPM_BUF_TRAIN_TARGET: p = cur_train_target(); b = train_target_.bytes(); break;
         case HPM_BUF_TRAIN_RING: p = ring_.ptr; b = ring_.bytes(); break;
         case HPM_BUF_INFER_FILTER: p = filter_.ptr; b = filter_.bytes(); break;
         case HPM_BUF_COUNTERS: p = counters_.ptr; b = counters_.bytes(); break;

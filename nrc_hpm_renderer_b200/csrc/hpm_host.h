@@ -31,7 +31,7 @@ public:
     void pass_gen_rays(const float frame_random[4]);
     void pass_prep_train(const float frame_random[4]);
     void pass_composite();
-    void sync() { NRCHPM_CUDA(cudaStreamSynchronize(stream_)); }
+    void sync() { NRCHPM_CUDA(cudaStreamSynchronize(stream_)); if (train_stream_) NRCHPM_CUDA(cudaStreamSynchronize(train_stream_)); }
     void stage_ms(float ms[7]);
     void buffer_info(int which, void** ptr, size_t* bytes);
     void read_buffer(int which, void* host, size_t bytes);
@@ -51,6 +51,15 @@ private:
     uint32_t n_pixels_ = 0, n_train_ = 0, n_filter_ = 0;
     DeviceBuffer<float4> output_, primary_color_;
     DeviceBuffer<float> info_, origin_, dir_, infer_in_, infer_out_, train_in_, train_target_, train_ray_;
+    // pipelined training (cfg.pipeline_train): Train() of frame N runs on its own stream while frame N+1 is tracked; the train
+    // records are double-buffered so that prep_train(N+1) does not overwrite what Train(N) still reads
+    DeviceBuffer<float> train_in2_, train_target2_;
+    cudaStream_t train_stream_ = nullptr;
+    cudaEvent_t ev_infer_done_ = nullptr, ev_train_done_ = nullptr;
+    bool train_in_flight_ = false;
+    int train_set_ = 0;
+    float* cur_train_in() { return train_set_ ? train_in2_.ptr : train_in_.ptr; }
+    float* cur_train_target() { return train_set_ ? train_target2_.ptr : train_target_.ptr; }
     DeviceBuffer<uint32_t> ring_, filter_, active_list_, active_count_, train_flags_, block_totals_;
     DeviceBuffer<unsigned long long> counters_;
     uint32_t* filter_host_ = nullptr;     // pinned

@@ -483,8 +483,9 @@ void NrcCache::optimizer_step(cudaStream_t s) {
 
 float NrcCache::loss() {
     if (!loss_valid_) {
-        NRCHPM_CUDA(cudaMemcpyAsync(&loss_host_, loss_dev_.ptr, sizeof(float), cudaMemcpyDeviceToHost, stream_));
-        NRCHPM_CUDA(cudaStreamSynchronize(stream_));
+        cudaStream_t s = loss_stream_set_ ? loss_stream_ : stream_;       // the stream the last Train() ran on
+        NRCHPM_CUDA(cudaMemcpyAsync(&loss_host_, loss_dev_.ptr, sizeof(float), cudaMemcpyDeviceToHost, s));
+        NRCHPM_CUDA(cudaStreamSynchronize(s));
         loss_valid_ = true;
     }
     return loss_host_;
@@ -528,6 +529,7 @@ void NrcCache::run_inference(const uint32_t* filter_host) {
 }
 
 void NrcCache::run_train() {
+    loss_stream_set_ = false;
     const uint32_t B = cfg_.train_batch_size;
     for (uint32_t i = 0; i < cfg_.train_batch_count; i++) {                      // src/NeuralRadianceCache.cu:147-156
         if (peer_world_ >= 2) {
@@ -537,6 +539,21 @@ void NrcCache::run_train() {
             optimizer_step(stream_);
         } else {
             training_step(train_in_ + 5 * (size_t)i * B, train_target_ + 3 * (size_t)i * B, B, true, stream_);
+        }
+    }
+}
+
+// Train() on caller-supplied record buffers and stream (pipelined frames: hpm_render with pipeline_train)
+void NrcCache::run_train_on(const float* d_in, const float* d_target, cudaStream_t s) {
+    const uint32_t B = cfg_.train_batch_size;
+    loss_stream_ = s; loss_stream_set_ = true;
+    for (uint32_t i = 0; i < cfg_.train_batch_count; i++) {
+        if (peer_world_ >= 2) {
+            training_step(d_in + 5 * (size_t)i * B, d_target + 3 * (size_t)i * B, B, false, s);
+            peer_exchange(s);
+            optimizer_step(s);
+        } else {
+            training_step(d_in + 5 * (size_t)i * B, d_target + 3 * (size_t)i * B, B, true, s);
         }
     }
 }

@@ -59,6 +59,7 @@ public:
     void infer_and_train_host(const float* h_in, float* h_out, uint32_t n, const float* h_tin, const float* h_tgt, uint32_t B, uint32_t n_batches,
                               bool use_ema, float* loss_out);
     void set_stream_for_loss(cudaStream_t s) { if (!initialised_) stream_ = s; }
+    void run_train_on(const float* d_in, const float* d_target, cudaStream_t s);
 
     void get_params(int which, float* out);
     void set_params_fp32(const float* host_master);
@@ -98,6 +99,7 @@ private:
     const float* dw_source_ = nullptr;
     bool grid_grad_dirty_ = false, grads_pending_ = false, keep_dx_ = true, loss_valid_ = true, initialised_ = false;
     float loss_host_ = 0;
+    cudaStream_t loss_stream_ = nullptr; bool loss_stream_set_ = false;
     float* loss_pinned_ = nullptr;                   // pinned landing word of the loss for the host pipeline
     // en::NeuralRadianceCache::Init state
     uint32_t infer_count_ = 0;

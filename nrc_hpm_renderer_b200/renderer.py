@@ -76,7 +76,7 @@ class HpmScene:
 
 
 def make_render_config(width, height, app: AppConfig, *, blend=False, show_nrc=True, compact_inference=True, train_pixels=None,
-                       parity_q2=True, parity_q3=True, x_begin=0, x_end=0) -> _lib.RenderConfig:
+                       parity_q2=True, parity_q3=True, x_begin=0, x_end=0, pipeline_train=False) -> _lib.RenderConfig:
     """Specialization constants of NrcHpmRenderer::InitSpecializationConstants (reference src/NrcHpmRenderer.cu:908-1061).
     parity_q2: the reference never passes TRAIN_RAY_LENGTH, shaders see 1.
     parity_q3: TRAIN_Y_DIST receives trainXDist."""
@@ -96,6 +96,7 @@ def make_render_config(width, height, app: AppConfig, *, blend=False, show_nrc=T
     c.infer_batch_size = app.infer_batch_size
     c.blend, c.show_nrc, c.compact_inference = int(blend), int(show_nrc), int(compact_inference)
     c.x_begin, c.x_end = x_begin, x_end
+    c.pipeline_train = int(pipeline_train)     # Train(N) underneath the tracking of frame N+1 (same order of effects)
     return c
 
 

@@ -231,3 +231,30 @@ def test_tracker_logf_is_the_library_logf_on_every_reachable_argument():
     n = C.c_uint64(123)
     _lib.check(_lib.lib().hpm_selftest_logf(C.byref(n)))
     assert n.value == 0
+
+
+def test_pipelined_training_keeps_the_order_of_effects(oracle_lib):
+    """pipeline_train: Train() of frame N runs on its own stream underneath the tracking of frame N+1.  With an encoding without
+    parameters (no atomics: training is deterministic) the frames and the final parameters are bit-identical to the serial renderer."""
+    from nrc_hpm_renderer_b200 import AppConfig, Camera, HpmSceneConfig
+    from nrc_hpm_renderer_b200 import nrc as N, renderer as R
+    grid = np.ascontiguousarray(golden("wdas_cloud_sixteenth_u8.npz")["data"])
+    W, H = 128, 64
+    runs = []
+    for pipelined in (False, True):
+        app = AppConfig.default(); app.scene = HpmSceneConfig.preset(0)
+        app.pos_enc_id, app.log2_train_batch_size, app.train_batch_count = 2, 9, 2
+        nrc = N.NeuralRadianceCache(app)
+        scene = R.HpmScene(grid, app.scene)
+        cfg = R.make_render_config(W, H, app, train_pixels=1024, pipeline_train=pipelined, parity_q2=False)
+        r = R.NrcHpmRenderer(W, H, False, Camera(aspect=W / H), app, scene, nrc, render_config=cfg)
+        frames = []
+        for f in range(6):
+            r.Render(True, FR + np.float32(0.07 * f))
+            frames.append(r.GetImage().copy())
+        r.sync()
+        runs.append((frames, nrc.get_params(N.MASTER), nrc.get_params(N.EMA), nrc.GetLoss()))
+    for a, b in zip(runs[0][0], runs[1][0]):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert np.array_equal(runs[0][1], runs[1][1]) and np.array_equal(runs[0][2], runs[1][2]) and runs[0][3] == runs[1][3]
+    assert np.any(runs[0][0][5] != runs[0][0][0])
