@@ -227,6 +227,7 @@ NrcCache::NrcCache(const NrcConfig& cfg, uint64_t seed) : cfg_(cfg) {
 NrcCache::~NrcCache() {
     for (auto e : pipe_events_) cudaEventDestroy(e);
     if (loss_pinned_) cudaFreeHost(loss_pinned_);
+    if (opt_side_stream_) { cudaStreamDestroy(opt_side_stream_); cudaEventDestroy(opt_fork_); cudaEventDestroy(opt_join_); }
     if (copy_in_stream_) { cudaStreamDestroy(copy_in_stream_); cudaStreamDestroy(copy_out_stream_); cudaStreamDestroy(compute_stream_); cudaStreamDestroy(train_stream_); }
 }
 
@@ -471,11 +472,25 @@ void NrcCache::optimizer_step(cudaStream_t s) {
     a.ema_debias_old = 1 - (float)std::pow(cfg_.ema_decay, current_step_ - 1);          // ema.h:105-108
     a.ema_debias_new = 1.0f / (1 - (float)std::pow(cfg_.ema_decay, current_step_));
     NRCHPM_REQUIRE(n_mlp_ % 256 == 0, "optimizer: the network parameter count must be a multiple of 256");
-    nrc_optimizer_kernel<true><<<(unsigned)((n_mlp_ + 2047) / 2048), 256, 0, s>>>(a);
-    check_launch("nrc_optimizer_kernel<mlp>");
     if (n_params_ > n_mlp_) {
+        // the two instances touch disjoint parameters: the small, latency-bound network instance (12 CTAs, ~10 us) runs on a side
+        // stream next to the encoding instance instead of in front of it
+        if (!opt_side_stream_) {
+            NRCHPM_CUDA(cudaStreamCreateWithFlags(&opt_side_stream_, cudaStreamNonBlocking));
+            NRCHPM_CUDA(cudaEventCreateWithFlags(&opt_fork_, cudaEventDisableTiming));
+            NRCHPM_CUDA(cudaEventCreateWithFlags(&opt_join_, cudaEventDisableTiming));
+        }
+        NRCHPM_CUDA(cudaEventRecord(opt_fork_, s));
+        NRCHPM_CUDA(cudaStreamWaitEvent(opt_side_stream_, opt_fork_, 0));
+        nrc_optimizer_kernel<true><<<(unsigned)((n_mlp_ + 2047) / 2048), 256, 0, opt_side_stream_>>>(a);
+        check_launch("nrc_optimizer_kernel<mlp>");
+        NRCHPM_CUDA(cudaEventRecord(opt_join_, opt_side_stream_));
         nrc_optimizer_kernel<false><<<(unsigned)(((n_params_ - n_mlp_) / 8 + 255) / 256), 256, 0, s>>>(a);
         check_launch("nrc_optimizer_kernel<encoding>");
+        NRCHPM_CUDA(cudaStreamWaitEvent(s, opt_join_, 0));
+    } else {
+        nrc_optimizer_kernel<true><<<(unsigned)((n_mlp_ + 2047) / 2048), 256, 0, s>>>(a);
+        check_launch("nrc_optimizer_kernel<mlp>");
     }
     grid_grad_dirty_ = false;       // the optimizer re-zeroes every encoding gradient it consumed
     grads_pending_ = false;

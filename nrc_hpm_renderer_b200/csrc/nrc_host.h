@@ -100,7 +100,8 @@ private:
     bool grid_grad_dirty_ = false, grads_pending_ = false, keep_dx_ = true, loss_valid_ = true, initialised_ = false;
     float loss_host_ = 0;
     cudaStream_t loss_stream_ = nullptr; bool loss_stream_set_ = false;
-    float* loss_pinned_ = nullptr;                   // pinned landing word of the loss for the host pipeline
+    float* loss_pinned_ = nullptr;
+    cudaStream_t opt_side_stream_ = nullptr; cudaEvent_t opt_fork_ = nullptr, opt_join_ = nullptr;   // network-weight optimizer instance                   // pinned landing word of the loss for the host pipeline
     // en::NeuralRadianceCache::Init state
     uint32_t infer_count_ = 0;
     float *infer_in_ = nullptr, *infer_out_ = nullptr, *train_in_ = nullptr, *train_target_ = nullptr;
