@@ -24,6 +24,27 @@ def rel_err(a, b, floor=1.0):
     return float(np.max(np.abs(a[ok] - b[ok]) / scale)) if ok.any() else 0.0
 
 
+def contract_distribution(a, b, floor=1e-2):
+    """error distribution under the contract metric of SURVEY.md 8(d): |a-b| / max(|b|, 1e-2 rms(b)) per output element"""
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    ok = np.isfinite(b)
+    e = np.abs(a[ok] - b[ok]) / np.maximum(np.abs(b[ok]), floor * np.sqrt(np.mean(b[ok] ** 2)) + 1e-30)
+    return {"p50": float(np.percentile(e, 50)), "p99": float(np.percentile(e, 99)), "p99.9": float(np.percentile(e, 99.9)), "max": float(e.max()),
+            "frac_gt_1e-2": float((e > 1e-2).mean())}
+
+
+def report_parity(name, what, ours, baseline):
+    """append the measured distribution to gpurun_out/parity_contract.jsonl (copied to profiles/ by the builder)"""
+    import json, os
+    from conftest import ROOT
+    d = os.path.join(ROOT, "gpurun_out")
+    line = {"config": name, "what": what, "metric": "|a-b| / max(|b|, 1e-2 rms(b))", "cuda_path_vs_tcnn": ours, "oracle_fp32_accumulation_vs_tcnn": baseline}
+    print(json.dumps(line))
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_contract.jsonl"), "a") as f:
+            f.write(json.dumps(line) + "\n")
+
+
 def make_cache(z, **kw):
     import torch  # noqa: F401
     from nrc_hpm_renderer_b200 import AppConfig
@@ -81,6 +102,21 @@ def test_inference_vs_tcnn(name):
     c.inference(dev(z["infer_in"]), out, n, use_ema=False)
     torch.cuda.synchronize()
     assert rel_err(out.cpu().numpy(), z["infer_working_step0"], floor=1.0) <= 1e-2
+    # ---- the same outputs under SURVEY.md 8(d)'s contract metric |a-b| / max(|b|, 1e-2 rms): reported as a distribution, and
+    # bounded by what a FAITHFUL restatement with the CUDA path's arithmetic (fp32 accumulation) reaches against the same fixture.
+    # Measured on the CPU (oracle vs these fixtures): even in tcnn's own fp16-accumulation mode, where the oracle reproduces
+    # 99.9 % of tcnn's outputs bit for bit, the maximum is 1.2e-2 (hash_ob_d6) / 3.1e-2 (tri_ob_d5); in fp32 mode p99 is 8e-3 / 7.8e-2:
+    # outputs two decades below the rms are differences of O(rms) terms rounded to fp16 (ulp 5e-4 relative) layer by layer.
+    import oracle as O
+    o = O.NrcOracle(O.nrc_config(int(z["pos"]), int(z["dir"]), int(z["depth"]), accum_fp16=0))
+    ref = z["infer_working_step0"]
+    dist = contract_distribution(out.cpu().numpy(), ref)
+    base = contract_distribution(o.inference(z["infer_in"], use_ema=False), ref)
+    report_parity(name, "inference_vs_tcnn", dist, base)
+    if name != "freq_ob_d4":          # Frequency: tcnn evaluates __sinf (frequency.h:74) on arguments up to 2^11 pi; covered by the rms-floored bound above
+        assert dist["p50"] <= 2.5e-3
+        assert dist["p99"] <= max(1e-2, 1.5 * base["p99"]), (dist, base)
+        assert dist["frac_gt_1e-2"] <= base["frac_gt_1e-2"] + 0.02, (dist, base)
 
 
 @pytest.mark.parametrize("name", CONFIGS)

@@ -18,10 +18,11 @@ FR = np.array([0.3183, 0.7071, 0.1234, 0.9876], np.float32)
 
 
 def setup(scene_id, W, H, oracle, *, train_pixels=1024, ring_frac=1.0, prl=1, prob=0.0, spp=1, trl=1, env=(0, 0, 0), compact=True, nrc=None, blend=False,
-          log2_infer_batch=None):
+          log2_infer_batch=None, grid=None, density=None):
     from nrc_hpm_renderer_b200 import AppConfig, Camera, HpmSceneConfig
     from nrc_hpm_renderer_b200.renderer import HpmScene, NrcHpmRenderer, make_render_config
-    grid = np.ascontiguousarray(golden("wdas_cloud_sixteenth_u8.npz")["data"])
+    if grid is None:
+        grid = np.ascontiguousarray(golden("wdas_cloud_sixteenth_u8.npz")["data"])
     app = AppConfig.default()
     app.scene = HpmSceneConfig.preset(scene_id)
     app.primary_ray_length, app.primary_ray_prob, app.train_spp, app.train_ring_buf_size = prl, prob, spp, ring_frac
@@ -29,7 +30,7 @@ def setup(scene_id, W, H, oracle, *, train_pixels=1024, ring_frac=1.0, prl=1, pr
     if log2_infer_batch is not None:
         app.log2_infer_batch_size = log2_infer_batch          # the renderer's filter granularity == the cache's batch size (one AppConfig)
     cam = Camera(aspect=W / H)
-    scene = HpmScene(grid, app.scene, env_color=env)
+    scene = HpmScene(grid, app.scene, env_color=env, density=density)
     cfg = make_render_config(W, H, app, blend=blend, compact_inference=compact, train_pixels=train_pixels, parity_q2=False)
     r = NrcHpmRenderer(W, H, blend, cam, app, scene, nrc, render_config=cfg)
     d = scene.desc
@@ -41,7 +42,9 @@ def setup(scene_id, W, H, oracle, *, train_pixels=1024, ring_frac=1.0, prl=1, pr
     return r, osc, ocfg, ocam
 
 
-@pytest.mark.parametrize("scene_id,prl,prob,env", [(0, 1, 0.0, (0, 0, 0)), (1, 1, 0.0, (0, 0, 0)), (4, 2, 0.5, (1, 1, 1)), (2, 0, 0.0, (0, 0, 0))])
+# last case = BASELINE config 4: the dense medium (scene-5 density 1.6, src/AppConfig.cpp:138-145) with the thesis' worst-case termination
+# (primaryRayLength 4, primaryRayProb .75: gen_rays.comp:39-42) -- long paths, the divergence / compaction stress case
+@pytest.mark.parametrize("scene_id,prl,prob,env", [(0, 1, 0.0, (0, 0, 0)), (1, 1, 0.0, (0, 0, 0)), (4, 2, 0.5, (1, 1, 1)), (2, 0, 0.0, (0, 0, 0)), (5, 4, 0.75, (1, 1, 1))])
 def test_gen_rays_vs_oracle(scene_id, prl, prob, env, oracle_lib):
     from nrc_hpm_renderer_b200 import renderer as R
     W, H = 160, 96

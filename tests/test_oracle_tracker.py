@@ -131,3 +131,82 @@ def test_mc_render_energy(oracle_lib):
         means.append(np.nanmean(acc[:, 0]))
         assert np.nanmin(acc) >= 0.0
     assert means[1] >= means[0] * 0.95
+
+
+# ---------------------------------------------------------------------------------------------- reference frames
+# The only outputs of the reference's tracker that exist are its converged frames reference/<scene>/0.exr (McHpmRenderer, path
+# length 64, 8192 blended frames, reference src/Reference.cpp:443-455, 581-598); tests/golden/exr_block8.npz holds their 8x8 block
+# means.  The CPU oracle's own path tracer (hpmo_mc_render: data/shader/mc/render.comp:7-84 over the same tracking functions that
+# gen_rays / prep_train_rays use) renders the same camera at 240x135 and is compared with them, which pins the oracle itself --
+# and through the bit-level oracle-vs-CUDA tests (tests/test_gpu_tracker.py) the CUDA tracker -- to reference OUTPUT.
+def _quarter_cloud():
+    import os
+    from conftest import ROOT
+    from nrc_hpm_renderer_b200 import volume
+    p = os.path.join(ROOT, "data", "wdas_cloud_quarter_u8.npz")
+    if not os.path.exists(p):
+        pytest.skip("data/wdas_cloud_quarter_u8.npz missing")
+    return volume.load_volume(p).data
+
+
+def _oracle_mc_frames(oracle, grid, scene_id, frames, *, density=None, point=None, env=(0, 0, 0), seed=1337):
+    from nrc_hpm_renderer_b200 import Camera, HpmSceneConfig, sky_size
+    from nrc_hpm_renderer_b200.renderer import dir_light_vec
+    W, H = 240, 135
+    d, h, w = grid.shape
+    sc = HpmSceneConfig.preset(scene_id)
+    osc = oracle.make_scene(grid, sky_size((w, h, d)), sc.density if density is None else density, 0.8, dir_light_vec(-1.57, 0.0), sc.dir_light_strength, (0, 0, 0),
+                            sc.point_light_strength if point is None else point, (1, 1, 1), sc.hdr_env_map_strength, env)
+    cfg = oracle.make_config(W, H, 0, 0, 1, 1)
+    cam = Camera(aspect=1920 / 1080)
+    ocam = oracle.make_camera(cam.inv_proj_view, cam.pos)
+    out = np.zeros((W * H, 4), np.float32)
+    rng = np.random.default_rng(seed)
+    for f in range(frames):
+        oracle.mc_render(osc, cfg, ocam, rng.random(4).astype(np.float32), 64, 1.0 / (f + 1), out)
+    return out.reshape(H, W, 4)
+
+
+@pytest.mark.parametrize("scene_id,env", [(0, (0, 0, 0)), (4, (1, 1, 1))])
+def test_oracle_path_tracer_matches_reference_exr(oracle_lib, scene_id, env):
+    """scenes whose EXR was rendered with the committed presets: mean radiance (Reference::Result relBias), opacity, image"""
+    ref = golden("exr_block8.npz")[f"s{scene_id}"].astype(np.float32)
+    img = _oracle_mc_frames(oracle_lib, _quarter_cloud(), scene_id, 48, env=env)
+    assert np.isfinite(img).all()
+    rad, alpha = img[..., 0], img[..., 3]
+    fg_ref, fg = ref[..., 1] > 0.02, alpha > 0.02
+    assert (fg_ref == fg).mean() >= 0.98
+    both = fg_ref & fg & (ref[..., 1] > 0.5)
+    rel_bias = (rad[both].mean() - ref[..., 0][both].mean()) / ref[..., 0][both].mean()
+    assert abs(rel_bias) <= 0.03, rel_bias                                   # thesis: rBias of the path tracer within +-0.01 (5.3.3)
+    assert abs(alpha[both].mean() - ref[..., 1][both].mean()) <= 0.02
+    a, b = rad[both].astype(np.float64), ref[..., 0][both].astype(np.float64)
+    assert np.corrcoef(a, b)[0, 1] >= 0.85                                   # 48 samples per pixel against the converged block means
+
+
+def test_reference_exr_scenes_1_2_5_parameters(oracle_lib):
+    """reference/1, 2, 5/0.exr were NOT rendered with the presets committed in src/AppConfig.cpp:102-141 -- named here.
+    The image SHAPE agrees with the committed shaders (ratio map flat over three decades of radiance), only a scalar differs:
+      scene 1: pointLightStrength 20 instead of 64 (committed value: 3.2x brighter everywhere);
+      scene 2: pointLightStrength 64 instead of 128 (committed: 1.95x brighter);
+      scene 5: density 0.8 -- the value in the source comment `density = 1.6f; // 0.8` -- reproduces the EXR's opacity (1.6 does not);
+               its in-scattered radiance is 1.8x below the committed shader at ANY density while its background is exactly 1.0,
+               i.e. it predates the committed environment-light code (the commented-out hdrEnvMapData.hpmStrength variant,
+               data/shader/include/path_trace.glsl:110-126) and is not reproducible from the repository.
+    Radiance is linear in the light strength, so the point-light EXRs remain usable goldens after rescaling."""
+    grid = _quarter_cloud()
+    refs = golden("exr_block8.npz")
+    for scene_id, strength, frames in ((1, 20.0, 96), (2, 64.0, 160)):
+        ref = refs[f"s{scene_id}"].astype(np.float32)
+        img = _oracle_mc_frames(oracle_lib, grid, scene_id, frames, point=strength)
+        both = (ref[..., 1] > 0.5) & (img[..., 3] > 0.5)
+        ratio = img[..., 0][both].mean() / ref[..., 0][both].mean()
+        assert abs(ratio - 1.0) <= 0.08, (scene_id, ratio)                   # point-light frames are heavy-tailed (thesis rVar 5.4)
+        assert abs(img[..., 3][both].mean() - ref[..., 1][both].mean()) <= 0.02
+    ref = refs["s5"].astype(np.float32)
+    alpha_err = {}
+    for density in (0.8, 1.6):
+        img = _oracle_mc_frames(oracle_lib, grid, 5, 16, density=density, env=(1, 1, 1))
+        both = (ref[..., 1] > 0.5) & (img[..., 3] > 0.5)
+        alpha_err[density] = abs(img[..., 3][both].mean() - ref[..., 1][both].mean())
+    assert alpha_err[0.8] <= 0.005 and alpha_err[1.6] >= 0.015, alpha_err
