@@ -122,6 +122,12 @@ int nrc_optimizer_step(nrc_cache* c, void* stream);
 /* test hooks: tensors of the last training step.  which: 0 padded output __half[B][16], 1 dL/doutput __half[B][16],
  * 2 dL/dinput __half[B][input_width] (only when the position encoding has parameters). host_out receives floats. */
 int nrc_last_step_tensor(nrc_cache* c, int which, float* host_out);
+/* development aid: clock64 stamps of the last fused training launch, long long[ctas][16] (phase boundaries of thread 0 of every
+ * CTA); only recorded when the process runs with NRCHPM_TRAIN_PROF=1.  Returns the number of CTAs written (0: not recording). */
+uint32_t nrc_debug_train_profile(nrc_cache* c, long long* host_out, uint32_t max_ctas);
+/* development aid (NRCHPM_TRAIN_PROF=1): device-side timeline of the training kernels launched since the last call, in launch order
+ * (fused step, optimizer, EMA pass, ...): host_out[2k] = earliest CTA start, host_out[2k+1] = latest CTA end, %globaltimer ns. */
+uint32_t nrc_debug_timeline(nrc_cache* c, unsigned long long* host_out, uint32_t max_slots);
 
 /* Host-buffer entry points (pageable or pinned host memory; H2D and D2H copies happen inside the call). */
 int nrc_inference_host(nrc_cache* c, const float* h_in, float* h_out, uint32_t n, int use_ema);

@@ -76,6 +76,8 @@ SIGNATURES = {
     "nrc_training_step": (_I, [_P, _P, _P, _U32, _I, _P]),
     "nrc_optimizer_step": (_I, [_P, _P]),
     "nrc_last_step_tensor": (_I, [_P, _I, _F]),
+    "nrc_debug_train_profile": (_U32, [_P, _P, _U32]),
+    "nrc_debug_timeline": (_U32, [_P, _P, _U32]),
     "nrc_inference_host": (_I, [_P, _F, _F, _U32, _I]),
     "nrc_training_step_host": (_I, [_P, _F, _F, _U32, _F]),
     "nrc_infer_and_train_host": (_I, [_P, _F, _F, _U32, _F, _F, _U32, _U32, _I, _F]),

@@ -227,7 +227,11 @@ NrcCache::NrcCache(const NrcConfig& cfg, uint64_t seed) : cfg_(cfg) {
 NrcCache::~NrcCache() {
     for (auto e : pipe_events_) cudaEventDestroy(e);
     if (loss_pinned_) cudaFreeHost(loss_pinned_);
-    if (opt_side_stream_) { cudaStreamDestroy(opt_side_stream_); cudaEventDestroy(opt_fork_); cudaEventDestroy(opt_join_); }
+    if (ema_stream_) {
+        cudaStreamSynchronize(ema_stream_);
+        cudaStreamDestroy(ema_stream_);
+        cudaEventDestroy(adam_done_); cudaEventDestroy(ema_done_);
+    }
     if (copy_in_stream_) { cudaStreamDestroy(copy_in_stream_); cudaStreamDestroy(copy_out_stream_); cudaStreamDestroy(compute_stream_); cudaStreamDestroy(train_stream_); }
 }
 
@@ -253,6 +257,7 @@ void NrcCache::set_params_fp32(const float* host_master) {
 }
 
 void NrcCache::set_ema(const float* host_ema) {
+    NRCHPM_CUDA(cudaDeviceSynchronize());          // an EMA pass may still be running on its side stream
     std::vector<__half> h(n_params_);
     for (size_t i = 0; i < n_params_; i++) h[i] = __float2half_rn(host_ema[i]);
     NRCHPM_CUDA(cudaMemcpy(ema16_.ptr, h.data(), n_params_ * sizeof(__half), cudaMemcpyHostToDevice));
@@ -261,7 +266,7 @@ void NrcCache::set_ema(const float* host_ema) {
 void NrcCache::get_params(int which, float* out) {
     if (which == 3 && grads_pending_) {       // before the optimizer ran, the MLP gradient only exists as per-chunk partials
         const float* src = dw_source_ ? dw_source_ : dw_partials_.ptr;
-        nrc_partials_to_half_kernel<<<(unsigned)((n_mlp_ + 255) / 256), 256, 0, stream_>>>(src, dw_source_ ? 1u : dw_chunks_, (uint32_t)n_mlp_, grad16_.ptr);
+        nrc_partials_to_half_kernel<<<(unsigned)((n_mlp_ + 255) / 256), 256, 0, train_stream_last_>>>(src, dw_source_ ? 1u : dw_chunks_, (uint32_t)n_mlp_, grad16_.ptr);
         check_launch("nrc_partials_to_half_kernel");
     }
     NRCHPM_CUDA(cudaDeviceSynchronize());
@@ -313,10 +318,27 @@ void NrcCache::setup_kernels() {
         NRCHPM_CUDA(cudaFuncSetAttribute(nrc_forward2_kernel<IN_W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd2_smem_bytes<IN_W>(H, 3)));
         NRCHPM_CUDA(cudaFuncSetAttribute(nrc_forward2_kernel<IN_W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd2_smem_bytes<IN_W>(H, 1)));
         NRCHPM_CUDA(cudaFuncSetAttribute(nrc_backward2_kernel<IN_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd2_smem_bytes<IN_W>(H)));
+        if (fused_training_fits()) {
+            NRCHPM_CUDA(cudaFuncSetAttribute(nrc_train_fused_kernel<IN_W, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train_smem_bytes<IN_W>(H)));
+            NRCHPM_CUDA(cudaFuncSetAttribute(nrc_train_fused_kernel<IN_W, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train_smem_bytes<IN_W>(H)));
+        }
     });
     // tuning knobs (experiments only; the defaults are the measured best)
     if (const char* v = std::getenv("NRCHPM_INFER_GROUPS")) infer_groups_ = std::max(0, std::min(3, std::atoi(v)));
     if (const char* v = std::getenv("NRCHPM_TRAIN_GROUPS")) train_groups_ = std::max(0, std::min(1, std::atoi(v)));
+    if (const char* v = std::getenv("NRCHPM_TRAIN_FUSED")) train_fused_ = std::atoi(v) != 0;          // 0: the three-kernel path
+    if (const char* v = std::getenv("NRCHPM_TRAIN_TPR")) train_tpr_ = std::atoi(v) == 4 ? 4 : 2;      // threads per record of the fused kernel
+    if (const char* v = std::getenv("NRCHPM_TRAIN_PROF")) if (std::atoi(v)) { train_prof_.allocate((size_t)sm_count_ * 16); train_prof_.zero(); timeline_.allocate(2 * kTimelineSlots); reset_timeline(); }   // development aid
+}
+
+// the fused training kernel keeps one fp32 accumulator region per weight matrix in tensor memory and every hidden layer's
+// activations in shared memory: networks of up to six hidden layers (every configuration of the thesis) fit, deeper ones take the
+// three-kernel path
+bool NrcCache::fused_training_fits() const {
+    const int H = cfg_.n_hidden_layers;
+    size_t smem = 0;
+    NRC_DISPATCH_INW(enc_.in_w, { smem = train_smem_bytes<IN_W>(H); });
+    return train_tmem_cols(enc_.in_w, H) <= 512 && smem <= 227 * 1024;
 }
 
 // bytes of the coarse hash-grid levels the inference kernel stages in shared memory (0: none)
@@ -330,6 +352,7 @@ size_t NrcCache::infer_smem_level_bytes() const {
 // all-reduce of a training step is in flight; Inference() must still see the parameters of the previous frame).
 void NrcCache::snapshot_params(bool use_ema, cudaStream_t s) {
     infer_snapshot_.ensure(n_params_);
+    if (use_ema) wait_ema(s);
     NRCHPM_CUDA(cudaMemcpyAsync(infer_snapshot_.ptr, use_ema ? ema16_.ptr : w16_.ptr, n_params_ * sizeof(__half), cudaMemcpyDeviceToDevice, s));
     snapshot_valid_ = true;
 }
@@ -344,12 +367,14 @@ void NrcCache::inference_set(int param_set, const float* d_in, float* d_out, uin
 
 void NrcCache::encode(const float* d_in, uint32_t n, bool use_ema, void* d_out_half, cudaStream_t s) {
     if (n == 0) return;
+    if (use_ema) wait_ema(s);
     nrc_encode_kernel<<<(n + 127) / 128, 128, 0, s>>>(enc_, use_ema ? ema16_.ptr : w16_.ptr, (uint32_t)n_mlp_, d_in, n, (__half*)d_out_half);
     check_launch("nrc_encode_kernel");
 }
 
 void NrcCache::inference(const float* d_in, float* d_out, uint32_t n, bool use_ema, const uint32_t* d_indices, const uint32_t* d_count, cudaStream_t s) {
     if (n == 0) return;
+    if (use_ema && !infer_params_override_) wait_ema(s);
     FwdArgs a{};
     a.enc = enc_; a.params = infer_params_override_ ? infer_params_override_ : use_ema ? ema16_.ptr : w16_.ptr; a.n_mlp = (uint32_t)n_mlp_; a.n_hidden = cfg_.n_hidden_layers;
     a.in = d_in; a.indices = d_indices; a.d_count = d_count; a.n = n; a.out = d_out;
@@ -387,12 +412,15 @@ void NrcCache::launch_shape(uint32_t tiles, uint32_t& grid, uint32_t& threads) c
 void NrcCache::ensure_train_scratch(uint32_t B) {
     if (B <= scratch_batch_) return;
     const int H = cfg_.n_hidden_layers;
-    x16_.allocate((size_t)B * enc_.in_w);
-    acts_.allocate((size_t)H * B * kWidth);
-    dacts_.allocate((size_t)H * B * kWidth);
+    if (!(train_fused_ && fused_training_fits())) {       // the fused kernel keeps these in shared / tensor memory
+        x16_.allocate((size_t)B * enc_.in_w);
+        acts_.allocate((size_t)H * B * kWidth);
+        dacts_.allocate((size_t)H * B * kWidth);
+        dx16_.allocate((size_t)B * enc_.in_w);
+    }
     out16_.allocate((size_t)B * kOutPad);
     dout16_.allocate((size_t)B * kOutPad);
-    dx16_.allocate((size_t)B * enc_.in_w);
+    if (!train_done_.ptr) { train_done_.allocate(1); train_done_.zero(); }
     loss_partials_.allocate(B / kTile);
     dw_partials_.allocate((size_t)kMaxDwChunks * n_mlp_);
     scratch_batch_ = B;
@@ -403,6 +431,39 @@ void NrcCache::training_step(const float* d_in, const float* d_target, uint32_t 
     ensure_train_scratch(B);
     const int H = cfg_.n_hidden_layers;
     if (grid_grad_dirty_ && n_grid_) NRCHPM_CUDA(cudaMemsetAsync(grad16_.ptr + n_mlp_, 0, n_grid_ * sizeof(__half), s));   // grid.h:857-860
+    const uint32_t tiles = B / kTile;
+    if (train_fused_ && fused_training_fits()) {
+        // one launch: forward, loss, backward, weight gradients (per-CTA fp32 partials) and the hash-grid gradient scatter
+        TrainArgs a{};
+        a.enc = enc_; a.params = w16_.ptr; a.n_mlp = (uint32_t)n_mlp_; a.n_hidden = H;
+        a.in = d_in; a.target = d_target; a.n = B; a.loss_scale = cfg_.loss_scale;
+        a.grid_grad = n_grid_ ? grad16_.ptr + n_mlp_ : nullptr;
+        a.dw_partials = dw_partials_.ptr; a.loss_partials = loss_partials_.ptr; a.loss_out = loss_dev_.ptr; a.done_counter = train_done_.ptr;
+        a.out16 = out16_.ptr; a.dout16 = dout16_.ptr;
+        a.grid_state = n_grid_ ? grid_state_.ptr : nullptr;
+        a.prof = train_prof_.ptr;
+        a.tl = timeline_slot();
+        const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t)sm_count_);
+        if (train_tpr_ == 4) { NRC_DISPATCH_INW(enc_.in_w, { nrc_train_fused_kernel<IN_W, 4><<<grid, 512, train_smem_bytes<IN_W>(H), s>>>(a); }); }
+        else { NRC_DISPATCH_INW(enc_.in_w, { nrc_train_fused_kernel<IN_W, 2><<<grid, 256, train_smem_bytes<IN_W>(H), s>>>(a); }); }
+        check_launch("nrc_train_fused_kernel");
+        dw_chunks_ = grid;
+        grid_grad_dirty_ = n_grid_ != 0;
+    } else {
+        training_step_three_kernels(d_in, d_target, B, s);
+    }
+    last_batch_ = B;
+    dw_source_ = nullptr;
+    loss_valid_ = false;
+    grads_pending_ = true;
+    train_stream_last_ = s;
+    if (run_optimizer) optimizer_step(s);
+}
+
+// networks that do not fit the fused kernel (more than six hidden layers): forward / backward / weight-gradient kernels with the
+// activations in HBM between them
+void NrcCache::training_step_three_kernels(const float* d_in, const float* d_target, uint32_t B, cudaStream_t s) {
+    const int H = cfg_.n_hidden_layers;
     const uint32_t tiles = B / kTile;
     uint32_t grid, threads;
     launch_shape(tiles, grid, threads);
@@ -449,11 +510,6 @@ void NrcCache::training_step(const float* d_in, const float* d_target, uint32_t 
         NRC_DISPATCH_INW(enc_.in_w, { nrc_dw_kernel<IN_W><<<dim3(dw_chunks_, H + 1), 128, kDwSmemBytes, s>>>(a); });
         check_launch("nrc_dw_kernel");
     }
-    last_batch_ = B;
-    dw_source_ = nullptr;
-    loss_valid_ = false;
-    grads_pending_ = true;
-    if (run_optimizer) optimizer_step(s);
 }
 
 void NrcCache::optimizer_step(cudaStream_t s) {
@@ -471,39 +527,75 @@ void NrcCache::optimizer_step(cudaStream_t s) {
     a.log2_beta1 = std::log2(cfg_.beta1); a.log2_beta2 = std::log2(cfg_.beta2);
     a.ema_debias_old = 1 - (float)std::pow(cfg_.ema_decay, current_step_ - 1);          // ema.h:105-108
     a.ema_debias_new = 1.0f / (1 - (float)std::pow(cfg_.ema_decay, current_step_));
-    NRCHPM_REQUIRE(n_mlp_ % 256 == 0, "optimizer: the network parameter count must be a multiple of 256");
-    if (n_params_ > n_mlp_) {
-        // the two instances touch disjoint parameters: the small, latency-bound network instance (12 CTAs, ~10 us) runs on a side
-        // stream next to the encoding instance instead of in front of it
-        if (!opt_side_stream_) {
-            NRCHPM_CUDA(cudaStreamCreateWithFlags(&opt_side_stream_, cudaStreamNonBlocking));
-            NRCHPM_CUDA(cudaEventCreateWithFlags(&opt_fork_, cudaEventDisableTiming));
-            NRCHPM_CUDA(cudaEventCreateWithFlags(&opt_join_, cudaEventDisableTiming));
-        }
-        NRCHPM_CUDA(cudaEventRecord(opt_fork_, s));
-        NRCHPM_CUDA(cudaStreamWaitEvent(opt_side_stream_, opt_fork_, 0));
-        nrc_optimizer_kernel<true><<<(unsigned)((n_mlp_ + 2047) / 2048), 256, 0, opt_side_stream_>>>(a);
-        check_launch("nrc_optimizer_kernel<mlp>");
-        NRCHPM_CUDA(cudaEventRecord(opt_join_, opt_side_stream_));
-        nrc_optimizer_kernel<false><<<(unsigned)(((n_params_ - n_mlp_) / 8 + 255) / 256), 256, 0, s>>>(a);
-        check_launch("nrc_optimizer_kernel<encoding>");
-        NRCHPM_CUDA(cudaStreamWaitEvent(s, opt_join_, 0));
-    } else {
-        nrc_optimizer_kernel<true><<<(unsigned)((n_mlp_ + 2047) / 2048), 256, 0, s>>>(a);
-        check_launch("nrc_optimizer_kernel<mlp>");
+    a.tl = timeline_slot(); a.tl_ema = (n_params_ > n_mlp_) ? timeline_slot() : nullptr;
+    NRCHPM_REQUIRE(n_mlp_ % 1024 == 0, "optimizer: the network parameter count must be a multiple of 1024");
+    const bool has_grid = n_params_ > n_mlp_;
+    if (has_grid && !ema_stream_) {
+        NRCHPM_CUDA(cudaStreamCreateWithFlags(&ema_stream_, cudaStreamNonBlocking));
+        NRCHPM_CUDA(cudaEventCreateWithFlags(&adam_done_, cudaEventDisableTiming));
+        NRCHPM_CUDA(cudaEventCreateWithFlags(&ema_done_, cudaEventDisableTiming));
+    }
+    // ---- one launch: network weights (first n_mlp / 64 CTAs) + Adam on the touched hash-grid entries
+    if (ema_in_flight_) NRCHPM_CUDA(cudaStreamWaitEvent(s, ema_done_, 0));        // the previous step's EMA pass still reads the weights
+    a.mlp_blocks = (uint32_t)(n_mlp_ / 64);
+    const unsigned grid_blocks = has_grid ? (unsigned)(((n_params_ - n_mlp_) / 8 + 255) / 256) : 0u;
+    nrc_adam_kernel<<<a.mlp_blocks + grid_blocks, 256, 0, s>>>(a);
+    check_launch("nrc_adam_kernel");
+    if (has_grid) {
+        // ---- the dense EMA of the hash-grid weights, which only Inference() reads: side stream, underneath the next step
+        NRCHPM_CUDA(cudaEventRecord(adam_done_, s));
+        NRCHPM_CUDA(cudaStreamWaitEvent(ema_stream_, adam_done_, 0));
+        nrc_grid_ema_kernel<<<(unsigned)sm_count_, 256, 0, ema_stream_>>>(a);
+        check_launch("nrc_grid_ema_kernel");
+        NRCHPM_CUDA(cudaEventRecord(ema_done_, ema_stream_));
+        ema_in_flight_ = true;
     }
     grid_grad_dirty_ = false;       // the optimizer re-zeroes every encoding gradient it consumed
     grads_pending_ = false;
 }
 
+// the EMA weights are complete once the last nrc_grid_ema_kernel has finished: every reader of ema16_ orders itself behind it
+void NrcCache::wait_ema(cudaStream_t s) {
+    if (ema_in_flight_) NRCHPM_CUDA(cudaStreamWaitEvent(s, ema_done_, 0));
+}
+
 float NrcCache::loss() {
     if (!loss_valid_) {
-        cudaStream_t s = loss_stream_set_ ? loss_stream_ : stream_;       // the stream the last Train() ran on
+        cudaStream_t s = train_stream_last_;                              // the stream the last training step ran on
         NRCHPM_CUDA(cudaMemcpyAsync(&loss_host_, loss_dev_.ptr, sizeof(float), cudaMemcpyDeviceToHost, s));
         NRCHPM_CUDA(cudaStreamSynchronize(s));
         loss_valid_ = true;
     }
     return loss_host_;
+}
+
+// development aid (NRCHPM_TRAIN_PROF=1): clock64 stamps of the last fused training launch, [CTA][16]
+uint32_t NrcCache::train_profile(long long* host_out, uint32_t max_ctas) {
+    if (!train_prof_.ptr) return 0;
+    NRCHPM_CUDA(cudaDeviceSynchronize());
+    const uint32_t n = std::min<uint32_t>(max_ctas, (uint32_t)sm_count_);
+    NRCHPM_CUDA(cudaMemcpy(host_out, train_prof_.ptr, (size_t)n * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return n;
+}
+// development aid: every kernel of the training path stamps (earliest CTA start, latest CTA end) in %globaltimer ns into its own slot,
+// in launch order: fused, adam, ema, fused, ... ; reading the log resets it
+unsigned long long* NrcCache::timeline_slot() {
+    if (!timeline_.ptr || tl_seq_ >= kTimelineSlots) return nullptr;
+    return timeline_.ptr + 2 * (tl_seq_++);
+}
+void NrcCache::reset_timeline() {
+    std::vector<unsigned long long> init(2 * kTimelineSlots);
+    for (uint32_t k = 0; k < kTimelineSlots; k++) { init[2 * k] = ~0ull; init[2 * k + 1] = 0ull; }
+    NRCHPM_CUDA(cudaMemcpy(timeline_.ptr, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    tl_seq_ = 0;
+}
+uint32_t NrcCache::read_timeline(unsigned long long* host_out, uint32_t max_slots) {
+    if (!timeline_.ptr) return 0;
+    NRCHPM_CUDA(cudaDeviceSynchronize());
+    const uint32_t n = std::min(max_slots, tl_seq_);
+    NRCHPM_CUDA(cudaMemcpy(host_out, timeline_.ptr, (size_t)n * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    reset_timeline();
+    return n;
 }
 
 void NrcCache::last_step_tensor(int which, float* host_out) {
@@ -512,7 +604,7 @@ void NrcCache::last_step_tensor(int which, float* host_out) {
     const __half* src; size_t n;
     if (which == 0) { src = out16_.ptr; n = (size_t)last_batch_ * kOutPad; }
     else if (which == 1) { src = dout16_.ptr; n = (size_t)last_batch_ * kOutPad; }
-    else if (which == 2) { NRCHPM_REQUIRE(n_grid_ && keep_dx_, "dL/dinput is only kept for encodings with parameters"); src = dx16_.ptr; n = (size_t)last_batch_ * enc_.in_w; }
+    else if (which == 2) { NRCHPM_REQUIRE(n_grid_ && keep_dx_ && dx16_.ptr, "dL/dinput is only kept by the three-kernel training path (NRCHPM_TRAIN_FUSED=0) for encodings with parameters"); src = dx16_.ptr; n = (size_t)last_batch_ * enc_.in_w; }
     else throw Error(NRCHPM_ERR_INVALID, "nrc_last_step_tensor: which must be 0..2");
     std::vector<__half> h(n);
     NRCHPM_CUDA(cudaMemcpy(h.data(), src, n * sizeof(__half), cudaMemcpyDeviceToHost));
@@ -544,7 +636,6 @@ void NrcCache::run_inference(const uint32_t* filter_host) {
 }
 
 void NrcCache::run_train() {
-    loss_stream_set_ = false;
     const uint32_t B = cfg_.train_batch_size;
     for (uint32_t i = 0; i < cfg_.train_batch_count; i++) {                      // src/NeuralRadianceCache.cu:147-156
         if (peer_world_ >= 2) {
@@ -561,7 +652,6 @@ void NrcCache::run_train() {
 // Train() on caller-supplied record buffers and stream (pipelined frames: hpm_render with pipeline_train)
 void NrcCache::run_train_on(const float* d_in, const float* d_target, cudaStream_t s) {
     const uint32_t B = cfg_.train_batch_size;
-    loss_stream_ = s; loss_stream_set_ = true;
     for (uint32_t i = 0; i < cfg_.train_batch_count; i++) {
         if (peer_world_ >= 2) {
             training_step(d_in + 5 * (size_t)i * B, d_target + 3 * (size_t)i * B, B, false, s);
@@ -655,7 +745,7 @@ int nrc_peer_setup(nrc_cache* c, int rank, int world, const uint8_t* all_handles
     return guard([&] { NRCHPM_REQUIRE(c && all_handles, "null argument"); c->impl.peer_setup(rank, world, all_handles); });
 }
 int nrc_peer_exchange(nrc_cache* c, void* stream) {
-    return guard([&] { NRCHPM_REQUIRE(c, "null cache"); c->impl.set_stream_for_loss((cudaStream_t)stream); c->impl.peer_exchange((cudaStream_t)stream); });
+    return guard([&] { NRCHPM_REQUIRE(c, "null cache"); c->impl.peer_exchange((cudaStream_t)stream); });
 }
 int nrc_set_inference_cta_limit(nrc_cache* c, uint32_t max_ctas) {
     return guard([&] { NRCHPM_REQUIRE(c, "null cache"); c->impl.set_inference_cta_limit(max_ctas); });
@@ -664,9 +754,11 @@ int nrc_snapshot_params(nrc_cache* c, int use_ema, void* stream) {
     return guard([&] { NRCHPM_REQUIRE(c, "null cache"); c->impl.snapshot_params(use_ema != 0, (cudaStream_t)stream); });
 }
 int nrc_training_step(nrc_cache* c, const float* d_in, const float* d_tgt, uint32_t batch, int run_opt, void* stream) {
-    return guard([&] { NRCHPM_REQUIRE(c && d_in && d_tgt, "null argument"); c->impl.set_stream_for_loss((cudaStream_t)stream); c->impl.training_step(d_in, d_tgt, batch, run_opt != 0, (cudaStream_t)stream); });
+    return guard([&] { NRCHPM_REQUIRE(c && d_in && d_tgt, "null argument"); c->impl.training_step(d_in, d_tgt, batch, run_opt != 0, (cudaStream_t)stream); });
 }
 int nrc_optimizer_step(nrc_cache* c, void* stream) { return guard([&] { NRCHPM_REQUIRE(c, "null cache"); c->impl.optimizer_step((cudaStream_t)stream); }); }
+uint32_t nrc_debug_train_profile(nrc_cache* c, long long* out, uint32_t max_ctas) { uint32_t n = 0; guard([&] { NRCHPM_REQUIRE(c && out, "null argument"); n = c->impl.train_profile(out, max_ctas); }); return n; }
+uint32_t nrc_debug_timeline(nrc_cache* c, unsigned long long* out, uint32_t max_slots) { uint32_t n = 0; guard([&] { NRCHPM_REQUIRE(c && out, "null argument"); n = c->impl.read_timeline(out, max_slots); }); return n; }
 int nrc_last_step_tensor(nrc_cache* c, int which, float* out) { return guard([&] { NRCHPM_REQUIRE(c && out, "null argument"); c->impl.last_step_tensor(which, out); }); }
 
 int nrc_inference_host(nrc_cache* c, const float* h_in, float* h_out, uint32_t n, int use_ema) {
@@ -692,7 +784,8 @@ void NrcCache::gradient_buffers(float** mlp, void** enc) {
     NRCHPM_REQUIRE(grads_pending_, "nrc_gradient_buffers: call nrc_training_step(run_optimizer=0) first");
     if (!dw_source_) {
         mlp_grad_f32_.ensure(n_mlp_);
-        nrc_reduce_partials_kernel<<<(unsigned)((n_mlp_ + 255) / 256), 256, 0, stream_>>>(dw_partials_.ptr, dw_chunks_, (uint32_t)n_mlp_, mlp_grad_f32_.ptr);
+        // on the stream of the training step that produced the partials (not the cache's own stream: the caller may train elsewhere)
+        nrc_reduce_partials_kernel<<<(unsigned)((n_mlp_ + 63) / 64), 256, 0, train_stream_last_>>>(dw_partials_.ptr, dw_chunks_, (uint32_t)n_mlp_, mlp_grad_f32_.ptr);
         check_launch("nrc_reduce_partials_kernel");
         dw_source_ = mlp_grad_f32_.ptr;
     }
@@ -728,7 +821,7 @@ void NrcCache::peer_setup(int rank, int world, const uint8_t* handles) {
 void NrcCache::peer_exchange(cudaStream_t s) {
     NRCHPM_REQUIRE(peer_world_ >= 2, "nrc_peer_exchange before nrc_peer_setup");
     NRCHPM_REQUIRE(grads_pending_ && !dw_source_, "nrc_peer_exchange: call nrc_training_step(run_optimizer=0) first");
-    nrc_reduce_partials_kernel<<<(unsigned)((n_mlp_ + 255) / 256), 256, 0, s>>>(dw_partials_.ptr, dw_chunks_, (uint32_t)n_mlp_, mlp_grad_f32_.ptr);
+    nrc_reduce_partials_kernel<<<(unsigned)((n_mlp_ + 63) / 64), 256, 0, s>>>(dw_partials_.ptr, dw_chunks_, (uint32_t)n_mlp_, mlp_grad_f32_.ptr);
     check_launch("nrc_reduce_partials_kernel");
     PeerArgs a{};
     a.rank = peer_rank_; a.world = peer_world_; a.token = ++peer_token_;
@@ -826,6 +919,7 @@ void NrcCache::infer_and_train_host(const float* h_in, float* h_out, uint32_t n,
     NRCHPM_CUDA(cudaStreamWaitEvent(copy_in_stream_, ev_prev, 0));
     if (overlap) {
         infer_snapshot_.ensure(n_params_);
+        if (use_ema) wait_ema(compute_stream_);
         NRCHPM_CUDA(cudaMemcpyAsync(infer_snapshot_.ptr, use_ema ? ema16_.ptr : w16_.ptr, n_params_ * sizeof(__half), cudaMemcpyDeviceToDevice, compute_stream_));
         NRCHPM_CUDA(cudaEventRecord(ev_snap, compute_stream_));
         NRCHPM_CUDA(cudaStreamWaitEvent(train_stream_, ev_snap, 0));        // training overwrites what the snapshot copy reads

@@ -58,7 +58,6 @@ public:
     void training_step_host(const float* h_in, const float* h_tgt, uint32_t B, float* loss_out);
     void infer_and_train_host(const float* h_in, float* h_out, uint32_t n, const float* h_tin, const float* h_tgt, uint32_t B, uint32_t n_batches,
                               bool use_ema, float* loss_out);
-    void set_stream_for_loss(cudaStream_t s) { if (!initialised_) stream_ = s; }
     void run_train_on(const float* d_in, const float* d_target, cudaStream_t s);
 
     void get_params(int which, float* out);
@@ -71,6 +70,8 @@ public:
     void peer_setup(int rank, int world, const uint8_t* handles);
     void peer_exchange(cudaStream_t s);
     void last_step_tensor(int which, float* host_out);
+    uint32_t train_profile(long long* host_out, uint32_t max_ctas);
+    uint32_t read_timeline(unsigned long long* host_out, uint32_t max_slots);
     void keep_dx(bool k) { keep_dx_ = k; }
     cudaStream_t stream() const { return stream_; }
 
@@ -80,6 +81,8 @@ private:
     void setup_kernels();
     void scatter_grid_field(int field, const float* d_src);
     void ensure_train_scratch(uint32_t B);
+    bool fused_training_fits() const;
+    void training_step_three_kernels(const float* d_in, const float* d_target, uint32_t B, cudaStream_t s);
     void launch_shape(uint32_t tiles, uint32_t& grid, uint32_t& threads) const;
     void ensure_pipeline(uint32_t n_chunks);
     void queue_inference_pipeline(const float* h_in, float* h_out, uint32_t n, bool use_ema, uint32_t chunk, uint32_t n_chunks);
@@ -99,9 +102,20 @@ private:
     const float* dw_source_ = nullptr;
     bool grid_grad_dirty_ = false, grads_pending_ = false, keep_dx_ = true, loss_valid_ = true, initialised_ = false;
     float loss_host_ = 0;
-    cudaStream_t loss_stream_ = nullptr; bool loss_stream_set_ = false;
+    cudaStream_t train_stream_last_ = nullptr;       // stream of the last training step: loss(), gradient_buffers() order themselves behind it
+    bool train_fused_ = true; int train_tpr_ = 2;
+    DeviceBuffer<unsigned int> train_done_;
+    DeviceBuffer<long long> train_prof_;
+    DeviceBuffer<unsigned long long> timeline_;
+    static constexpr uint32_t kTimelineSlots = 256;
+    uint32_t tl_seq_ = 0;
+    unsigned long long* timeline_slot();
+    void reset_timeline();
     float* loss_pinned_ = nullptr;
-    cudaStream_t opt_side_stream_ = nullptr; cudaEvent_t opt_fork_ = nullptr, opt_join_ = nullptr;   // network-weight optimizer instance                   // pinned landing word of the loss for the host pipeline
+    cudaStream_t ema_stream_ = nullptr;              // dense EMA pass of the encoding weights, underneath the next training step
+    cudaEvent_t adam_done_ = nullptr, ema_done_ = nullptr;
+    bool ema_in_flight_ = false;
+    void wait_ema(cudaStream_t s);
     // en::NeuralRadianceCache::Init state
     uint32_t infer_count_ = 0;
     float *infer_in_ = nullptr, *infer_out_ = nullptr, *train_in_ = nullptr, *train_target_ = nullptr;

@@ -41,6 +41,9 @@
 #ifndef NRC_TRAIN_UNROLL
 #define NRC_TRAIN_UNROLL 2           // levels per round in the (latency-bound, low-occupancy) training forward kernel
 #endif
+#ifndef NRC_TRAIN_PREFETCH
+#define NRC_TRAIN_PREFETCH 0         // fused training kernel: prefetch the Adam records of the touched hash-grid entries into L2
+#endif
 
 namespace nrchpm {
 
@@ -128,7 +131,7 @@ __device__ __forceinline__ __half2 encode_level_smem(const EncParams& e, int l, 
 //    aliasing corners are never loaded; they take the value of their twin through a select.
 template <int UNROLL, bool POW2, class Put>
 __device__ __forceinline__ void hashgrid_levels(const EncParams& e, const __half2* __restrict__ grid, float x0, float x1, float x2,
-                                                int l_begin, int l_end, Put& put) {
+                                                int l_begin, int l_end, Put& put, const GridAdamState* pf_state = nullptr) {
 #if NRC_GATHER_BITS == 128
     typedef uint4 wide_t;
     constexpr uint32_t kGroupMask = 3u;
@@ -148,6 +151,11 @@ __device__ __forceinline__ void hashgrid_levels(const EncParams& e, const __half
             const int l = on ? l0 + u : l_end - 1;
             grid_level_cell<POW2>(e, l, x0, x1, x2, c[u]);
             const __half2* base = grid + e.level_offset[l];
+            if (pf_state) {      // training: the optimizer will update exactly these entries -- pull their Adam records into L2 (fire-and-forget)
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (on) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_state + e.level_offset[l] + c[u].idx[k]));
+            }
             const uint32_t hs_m = e.level_hsize[l] - 1u;
             const bool lin = e.level_hash[l] == 0 && (e.level_hsize[l] & hs_m) == 0;
             dupz[u] = lin && (e.level_s2[l] & hs_m) == 0;
@@ -337,13 +345,13 @@ __device__ __forceinline__ void hashgrid_pipelined(const EncParams& e, const __h
 // UNROLL > 0: rounds of UNROLL levels; UNROLL == 0: the software-pipelined flavour (needs ~128 registers: inference kernel only)
 template <int UNROLL = 2, class Put>
 __device__ __forceinline__ void encode_position(const EncParams& e, const __half2* __restrict__ grid, float x0, float x1, float x2,
-                                                int l_begin, int l_end, Put& put) {
+                                                int l_begin, int l_end, Put& put, const GridAdamState* pf_state = nullptr) {
     if (e.pos_enc == POS_HASHGRID) {
         constexpr int U = UNROLL > 0 ? UNROLL : 2;
         if (e.all_pow2) {
             if (UNROLL == 0) hashgrid_pipelined(e, grid, x0, x1, x2, l_begin, l_end, put);
-            else hashgrid_levels<U, true>(e, grid, x0, x1, x2, l_begin, l_end, put);
-        } else hashgrid_levels<U, false>(e, grid, x0, x1, x2, l_begin, l_end, put);
+            else hashgrid_levels<U, true>(e, grid, x0, x1, x2, l_begin, l_end, put, pf_state);
+        } else hashgrid_levels<U, false>(e, grid, x0, x1, x2, l_begin, l_end, put, pf_state);
     } else if (e.pos_enc == POS_IDENTITY) {
         put.put(0, __float2half_rn(x0)); put.put(1, __float2half_rn(x1)); put.put(2, __float2half_rn(x2));
     } else if (e.pos_enc == POS_TRIANGLE) {
@@ -450,6 +458,11 @@ __global__ void __launch_bounds__(128) nrc_encode_kernel(const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------- helpers
+// development aid (NRCHPM_TRAIN_PROF=1): device-side timeline of a training step, tl[2k] = earliest start, tl[2k+1] = latest end of kernel k
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void timeline_begin(unsigned long long* tl, int k) { if (tl && threadIdx.x == 0) atomicMin(tl + 2 * k, global_ns()); }
+__device__ __forceinline__ void timeline_end(unsigned long long* tl, int k) { if (tl && threadIdx.x == 0) atomicMax(tl + 2 * k + 1, global_ns()); }
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // row-major [rows][K] fp16 matrix -> K-major canonical tile (B operand of the forward MMAs)
@@ -1330,12 +1343,403 @@ __global__ void __launch_bounds__(128, 1) nrc_dw_kernel(const __grid_constant__ 
     if (warp == 0) tmem_dealloc(tmem_base_s, 128);
 }
 
-__global__ void __launch_bounds__(256) nrc_reduce_partials_kernel(const float* __restrict__ partials, uint32_t n_chunks, uint32_t n_mlp, float* __restrict__ out) {
-    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= n_mlp) return;
+// ---------------------------------------------------------------------------------------------- fused training step
+// Forward, RelativeL2Luminance, backward, weight gradients and the hash-grid gradient scatter of ONE 128-record tile in ONE CTA
+// (replaces nrc_forward2_kernel<TRAIN> + nrc_backward2_kernel + nrc_dw_kernel and the three activation tensors they exchanged
+// through HBM).  Reference counterpart: Trainer::training_step -> forward / loss / backward (trainer.h:163-190), i.e.
+// kernel_grid, kernel_mlp_fused, relative_l2_luminance_loss, kernel_mlp_fused_backward, the split-K weight-gradient GEMMs
+// (fully_fused_mlp.cu:783-836) and kernel_grid_backward (grid.h:215-320).
+//
+//  * shared memory (192 KB for 64 x 6, 48 inputs): ONE image of the weights, the encoded tile X, the post-ReLU activations of
+//    every hidden layer, two buffers for the pre-activation gradients dY, the loss gradient.  Every tile is stored
+//    [record][feature] in the canonical no-swizzle core-matrix layout: 8 records x 8 features (16 bytes per record) per core
+//    matrix.  The same bytes serve as K-major operand when `feature` is the contraction dimension (forward: A = X, B = W) and as
+//    MN-major operand when `record` (dW = dY^T A: both operands) or `out` (backward: B = W read as [in][out]) is -- only the
+//    LBO / SBO fields of the descriptor swap roles (LBO = stride between core matrices along K, SBO = along M / N).
+//  * tensor memory (512 columns): 64 accumulator columns + 32 operand columns for the layer chain exactly as in the inference
+//    kernel, and one fp32 accumulator region per weight matrix (M = 64) that collects dW over ALL tiles of the CTA; it is
+//    written to the CTA's partial once, at the end (the optimizer adds the partials in a fixed order: deterministic).
+//  * TPR threads per record (2 or 4): warps w, w + 4, ... share a TMEM lane quadrant and split the accumulator columns of every
+//    epilogue, the hash-grid levels of the gathers and of the gradient scatter.
+//  * MMA issue order per backward layer: the chain MMA (dA_{l-1} = dY_l W_l) first, committed to `bar_mma`; then the weight-
+//    gradient MMAs of that layer, committed to `bar_dw[l & 1]`, which only guards the re-use of the dY buffer two layers later.
+struct TrainArgs {
+    EncParams enc;
+    const __half* params;       // working weights [network | encoding]
+    uint32_t n_mlp;
+    int n_hidden;
+    const float* in;            // records float[n][5]
+    const float* target;        // float[n][3]
+    uint32_t n;                 // multiple of 128
+    float loss_scale;
+    __half* grid_grad;          // fp16 gradient of the encoding parameters or null
+    float* dw_partials;         // [gridDim.x][n_mlp]
+    float* loss_partials;       // [n / 128]
+    float* loss_out;
+    unsigned int* done_counter; // zero before the first launch; the kernel leaves it zero
+    __half* out16;              // [n][16] network output (fp16 like tcnn's), kept for nrc_last_step_tensor
+    __half* dout16;             // [n][16] dL/doutput * loss_scale
+    const GridAdamState* grid_state;   // optimizer state of the encoding entries: prefetched into L2 for the entries this step touches
+    long long* prof;            // optional [gridDim.x][16] phase time stamps (clock64 of thread 0), development aid
+    unsigned long long* tl;     // optional device-side timeline (development aid)
+};
+#define NRC_PROF(k) do { if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 16 + (k)] = clock64(); } while (0)
+
+template <int IN_W>
+__host__ __device__ constexpr size_t train_smem_bytes(int n_hidden) {
+    return (size_t)IN_W * 128 + (size_t)(n_hidden - 1) * 8192 + 2048 + (size_t)IN_W * 256 + (size_t)n_hidden * 16384 + 2 * 16384 + 4096;
+}
+// TMEM columns: chain accumulator (64) + chain operand (32) + dW regions (IN_W, (H-1) x 64, 16)
+__host__ __device__ constexpr uint32_t train_tmem_cols(int in_w, int n_hidden) { return 96u + (uint32_t)in_w + (uint32_t)(n_hidden - 1) * 64u + 16u; }
+
+template <int N> struct TmemCols;
+template <> struct TmemCols<32> {
+    static __device__ __forceinline__ void ld(uint32_t t, uint32_t* r) { tc05::tmem_ld32(t, r); }
+    static __device__ __forceinline__ void st_half(uint32_t t, const uint32_t* r) { tc05::tmem_st16(t, r); }
+};
+template <> struct TmemCols<16> {
+    static __device__ __forceinline__ void ld(uint32_t t, uint32_t* r) { tc05::tmem_ld16(t, r); }
+    static __device__ __forceinline__ void st_half(uint32_t t, const uint32_t* r) { tc05::tmem_st8(t, r); }
+};
+
+template <int IN_W, int TPR>
+__global__ void __launch_bounds__(128 * TPR, 1) nrc_train_fused_kernel(const __grid_constant__ TrainArgs a) {
+    using namespace tc05;
+    constexpr int NT = 128 * TPR;
+    constexpr int CPT = 64 / TPR;                 // accumulator columns of a hidden layer per thread
+    constexpr int CH = CPT / 8;                   // 16-byte chunks (8 fp16 features) per thread and layer
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar_mma, bar_dw[2], wbar;
+    __shared__ uint32_t tmem_base_s, s_last;
+    __shared__ float loss_red[4];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int quad = warp & 3, part = warp >> 2, r = quad * 32 + lane;
+    const int H = a.n_hidden;
+    uint8_t* w0_s = smem;
+    uint8_t* wh_s = w0_s + IN_W * 128;
+    uint8_t* wo_s = wh_s + (H - 1) * 8192;
+    uint8_t* x_s = wo_s + 2048;
+    uint8_t* act_s = x_s + IN_W * 256;
+    uint8_t* dy_s = act_s + H * 16384;
+    uint8_t* do_s = dy_s + 2 * 16384;
+
+    NRC_PROF(0);
+    timeline_begin(a.tl, 0);
+    if (warp == 0) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+    if (tid == 0) { mbar_init(&bar_mma, 1); mbar_init(&bar_dw[0], 1); mbar_init(&bar_dw[1], 1); mbar_init(&wbar, NT); fence_mbar_init(); }
+    // the weights travel to shared memory while the first tile is encoded (see nrc_forward2_kernel)
+    copy_weights_kmajor_async(w0_s, a.params, kWidth, IN_W, tid, NT);
+    for (int l = 1; l < H; l++) copy_weights_kmajor_async(wh_s + (l - 1) * 8192, a.params + IN_W * kWidth + (l - 1) * kWidth * kWidth, kWidth, kWidth, tid, NT);
+    copy_weights_kmajor_async(wo_s, a.params + IN_W * kWidth + (H - 1) * kWidth * kWidth, kOutPad, kWidth, tid, NT);
+    bool weights_pending = true;
+    fence_before();
+    __syncthreads();
+    fence_after();
+
+    const uint32_t tbase = tmem_base_s;
+    const uint32_t tD = tbase, tA = tbase + 64, tW0 = tbase + 96, tWh = tW0 + IN_W, tWo = tWh + (uint32_t)(H - 1) * 64;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const uint32_t x_addr = smem_u32(x_s), w0_addr = smem_u32(w0_s), wh_addr = smem_u32(wh_s), wo_addr = smem_u32(wo_s);
+    const uint32_t act_addr = smem_u32(act_s), dy_addr = smem_u32(dy_s), do_addr = smem_u32(do_s);
+    const uint32_t idesc64 = make_idesc_f16(128, 64), idesc16 = make_idesc_f16(128, 16);                 // forward: B K-major
+    const uint32_t idesc64b = make_idesc_f16(128, 64, 0, 1), idescxb = make_idesc_f16(128, IN_W, 0, 1);  // backward: B MN-major
+    const uint32_t idw64 = make_idesc_f16(64, 64, 1, 1), idwx = make_idesc_f16(64, IN_W, 1, 1), idwo = make_idesc_f16(64, 16, 1, 1);
+    const __half2* grid = reinterpret_cast<const __half2*>(a.params + a.n_mlp);
+    const bool leader = tid == 0;
+    const bool hashgrid = a.enc.pos_enc == POS_HASHGRID;
+    const bool scatter = a.grid_grad != nullptr && hashgrid;
+    const int L = a.enc.n_levels;
+    const int lv_b = hashgrid ? (L * part) / TPR : 0, lv_e = hashgrid ? (L * (part + 1)) / TPR : L;
+    uint32_t ph_mma = 0, ph_dw[2] = {0, 0};
+    bool pend[2] = {false, false};
+    const uint32_t n_tiles = a.n / kTile;
+    const uint32_t row_off64 = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 16u;        // this record's row in a [128][64] tile
+    uint8_t* my_x = x_s + (r >> 3) * (IN_W * 16) + (r & 7) * 16;
+    uint32_t it = 0;
+    NRC_PROF(1);
+
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+        const uint32_t row = tile * kTile + r;
+        // the weight-gradient MMAs of the previous tile still read X and the activations
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+            if (pend[b]) { mbar_wait(&bar_dw[b], ph_dw[b]); ph_dw[b] ^= 1; pend[b] = false; }
+        const float* rp = a.in + 5 * (size_t)row;
+        const float x0 = rp[0], x1 = rp[1], x2 = rp[2], th = rp[3], ph = rp[4];
+        float tg[3] = {0, 0, 0};
+        if (part == 0) { const float* tp = a.target + 3 * (size_t)row; tg[0] = tp[0]; tg[1] = tp[1]; tg[2] = tp[2]; }
+        {
+            SmemRowPut put{my_x};
+            // the optimizer will update exactly the entries this record touches: their 32-byte Adam records are prefetched into L2 with
+            // the gathers (the DRAM round trips run underneath the MLP), so that nrc_grid_adam_kernel -- the other half of the step's
+            // critical path, bound by its dependent gradient -> state loads -- finds them on chip
+            const GridAdamState* pf = (NRC_TRAIN_PREFETCH && scatter) ? a.grid_state : nullptr;
+            if (hashgrid || part == 0) encode_position<NRC_TRAIN_UNROLL>(a.enc, grid, x0, x1, x2, lv_b, lv_e, put, pf);
+            if (part == TPR - 1) encode_direction_pad(a.enc, th, ph, put);
+        }
+        NRC_PROF(2);
+        if (weights_pending) { cp_async_wait_all(); fence_proxy_async_smem(); mbar_arrive(&wbar); }
+        fence_proxy_async_smem();
+        fence_before();
+        __syncthreads();
+        NRC_PROF(3);
+        if (leader) {
+            if (weights_pending) mbar_wait(&wbar, 0);
+            fence_after();
+#pragma unroll
+            for (int s = 0; s < IN_W / 16; s++)
+                mma_f16_ss(tD, make_smem_desc(x_addr + s * 256, 128, IN_W * 16), make_smem_desc(w0_addr + s * 256, 128, IN_W * 16), idesc64, s > 0);
+            mma_commit(&bar_mma);
+        }
+        weights_pending = false;
+        mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1;
+        fence_after();
+        NRC_PROF(4);
+
+        // ---------------- forward: hidden layers
+        for (int l = 0; l < H; l++) {
+            uint32_t acc[CPT], p[CPT / 2];
+            TmemCols<CPT>::ld(tD + lane_base + part * CPT, acc);
+            wait_ld();
+            if (l == 0) {     // tcnn's ReLU is max(x, 0) in fp16: NaN (Q5) -> 0; cvt.relu would keep it
+                const __half2 zero2 = __float2half2_rn(0.0f);
+#pragma unroll
+                for (int j = 0; j < CPT / 2; j++) {
+                    uint32_t v = pack_f16x2(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
+                    __half2 m = __hmax2(*reinterpret_cast<__half2*>(&v), zero2);
+                    p[j] = *reinterpret_cast<uint32_t*>(&m);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < CPT / 2; j++) p[j] = pack_relu_f16x2(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
+            }
+            TmemCols<CPT>::st_half(tA + lane_base + part * (CPT / 2), p);
+            uint8_t* arow = act_s + l * 16384 + row_off64 + part * CH * 128;
+#pragma unroll
+            for (int c = 0; c < CH; c++) *reinterpret_cast<int4*>(arow + c * 128) = make_int4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
+            wait_st();
+            fence_proxy_async_smem();
+            fence_before();
+            __syncthreads();
+            if (leader) {
+                fence_after();
+                if (l < H - 1) {
+#pragma unroll
+                    for (int s = 0; s < 4; s++) mma_f16_ts(tD, tA + s * 8, make_smem_desc(wh_addr + l * 8192 + s * 256, 128, 1024), idesc64, s > 0);
+                } else {
+#pragma unroll
+                    for (int s = 0; s < 4; s++) mma_f16_ts(tD, tA + s * 8, make_smem_desc(wo_addr + s * 256, 128, 1024), idesc16, s > 0);
+                }
+                mma_commit(&bar_mma);
+            }
+            mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1;
+            fence_after();
+        }
+
+        NRC_PROF(5);
+        // ---------------- output layer: loss and its gradient (relative_l2_luminance.h:40-88; n_total = batch * 3)
+        if (part == 0) {
+            uint32_t o[16];
+            tmem_ld16(tD + lane_base, o);
+            wait_ld();
+            uint32_t ph16[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) ph16[j] = pack_f16x2(__uint_as_float(o[2 * j]), __uint_as_float(o[2 * j + 1]));
+            float pr[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) pr[k] = __half2float(__float2half_rn(__uint_as_float(o[k])));
+            const float n_total = (float)(a.n * 3u);
+            const float lum = 0.299f * pr[0] + 0.587f * pr[1] + 0.114f * pr[2];
+            const float denom = lum * lum + 0.01f;
+            float loss = 0, gk[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float diff = pr[k] - tg[k];
+                loss += diff * diff / denom / n_total;
+                gk[k] = a.loss_scale * (2 * diff / denom) / n_total;
+            }
+            uint32_t g8[8] = {pack_f16x2(gk[0], gk[1]), pack_f16x2(gk[2], 0.0f), 0u, 0u, 0u, 0u, 0u, 0u};
+            tmem_st8(tA + lane_base, g8);
+            uint8_t* drow = do_s + (r >> 3) * 256 + (r & 7) * 16;
+            *reinterpret_cast<int4*>(drow) = make_int4(g8[0], g8[1], 0, 0);
+            *reinterpret_cast<int4*>(drow + 128) = make_int4(0, 0, 0, 0);
+            if (a.out16) {
+                int4* od = reinterpret_cast<int4*>(a.out16 + (size_t)row * kOutPad);
+                od[0] = make_int4(ph16[0], ph16[1], ph16[2], ph16[3]); od[1] = make_int4(ph16[4], ph16[5], ph16[6], ph16[7]);
+                int4* gd = reinterpret_cast<int4*>(a.dout16 + (size_t)row * kOutPad);
+                gd[0] = make_int4(g8[0], g8[1], 0, 0); gd[1] = make_int4(0, 0, 0, 0);
+            }
+            // deterministic per-tile loss sum: warp shuffle tree, then the four quadrants in order
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, s);
+            if (lane == 0) loss_red[quad] = loss;
+            wait_st();
+        }
+        fence_proxy_async_smem();
+        fence_before();
+        __syncthreads();
+        if (leader) {
+            fence_after();
+            a.loss_partials[tile] = ((loss_red[0] + loss_red[1]) + loss_red[2]) + loss_red[3];
+            // dA_{H-1} = dOut (K = 16) x W_out read as [in][out]
+            mma_f16_ts(tD, tA, make_smem_desc(wo_addr, 1024, 128), idesc64b, 0);
+            mma_commit(&bar_mma);
+            // dW_out^T [in][out] += A_{H-1}^T dOut   (M = 64 inputs, N = 16 outputs, K = 128 records)
+#pragma unroll
+            for (int s = 0; s < 8; s++)
+                mma_f16_ss(tWo, make_smem_desc(act_addr + (H - 1) * 16384 + s * 2048, 1024, 128), make_smem_desc(do_addr + s * 512, 256, 128), idwo, (it > 0 || s > 0) ? 1u : 0u);
+        }
+        mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1;
+        fence_after();
+
+        NRC_PROF(6);
+        // ---------------- backward: hidden layers
+        const bool need_dx = scatter;
+        for (int l = H - 1; l >= 0; l--) {
+            const int b = l & 1;
+            if (pend[b]) { mbar_wait(&bar_dw[b], ph_dw[b]); ph_dw[b] ^= 1; pend[b] = false; }      // dY buffer b is free again
+            uint32_t acc[CPT], p[CPT / 2];
+            int4 av[CH];
+            const uint8_t* arow = act_s + l * 16384 + row_off64 + part * CH * 128;
+#pragma unroll
+            for (int c = 0; c < CH; c++) av[c] = *reinterpret_cast<const int4*>(arow + c * 128);
+            TmemCols<CPT>::ld(tD + lane_base + part * CPT, acc);
+            wait_ld();
+            const uint32_t* aw = reinterpret_cast<const uint32_t*>(av);
+#pragma unroll
+            for (int j = 0; j < CPT / 2; j++) {
+                const float lo = (aw[j] & 0x0000ffffu) ? __uint_as_float(acc[2 * j]) : 0.0f;
+                const float hi = (aw[j] & 0xffff0000u) ? __uint_as_float(acc[2 * j + 1]) : 0.0f;
+                p[j] = pack_f16x2(lo, hi);
+            }
+            TmemCols<CPT>::st_half(tA + lane_base + part * (CPT / 2), p);
+            uint8_t* drow = dy_s + b * 16384 + row_off64 + part * CH * 128;
+#pragma unroll
+            for (int c = 0; c < CH; c++) *reinterpret_cast<int4*>(drow + c * 128) = make_int4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
+            wait_st();
+            fence_proxy_async_smem();
+            fence_before();
+            __syncthreads();
+            const bool chain = l > 0 || need_dx;
+            if (leader) {
+                fence_after();
+                if (l > 0) {
+#pragma unroll
+                    for (int s = 0; s < 4; s++) mma_f16_ts(tD, tA + s * 8, make_smem_desc(wh_addr + (l - 1) * 8192 + s * 2048, 1024, 128), idesc64b, s > 0);
+                } else if (need_dx) {
+#pragma unroll
+                    for (int s = 0; s < 4; s++) mma_f16_ts(tD, tA + s * 8, make_smem_desc(w0_addr + s * (IN_W * 32), IN_W * 16, 128), idescxb, s > 0);
+                }
+                if (chain) mma_commit(&bar_mma);
+                // dW_l [out][in] += dY_l^T A_{l-1}   (M = 64 outputs, N inputs, K = 128 records)
+                const uint32_t acc0 = it > 0 ? 1u : 0u;
+                if (l > 0) {
+#pragma unroll
+                    for (int s = 0; s < 8; s++)
+                        mma_f16_ss(tWh + (uint32_t)(l - 1) * 64, make_smem_desc(dy_addr + b * 16384 + s * 2048, 1024, 128), make_smem_desc(act_addr + (l - 1) * 16384 + s * 2048, 1024, 128), idw64, (s > 0) ? 1u : acc0);
+                } else {
+#pragma unroll
+                    for (int s = 0; s < 8; s++)
+                        mma_f16_ss(tW0, make_smem_desc(dy_addr + b * 16384 + s * 2048, 1024, 128), make_smem_desc(x_addr + s * (IN_W * 32), IN_W * 16, 128), idwx, (s > 0) ? 1u : acc0);
+                }
+                mma_commit(&bar_dw[b]);
+            }
+            pend[b] = true;
+            if (chain) { mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1; fence_after(); }
+        }
+
+        NRC_PROF(7);
+        // ---------------- hash-grid gradient: (half)weight * dL/dx, fp16x2 reductions (kernel_grid_backward, grid.h:215-320)
+        if (need_dx) {
+            __half2* gg = reinterpret_cast<__half2*>(a.grid_grad);
+#pragma unroll 1
+            for (int l = lv_b; l < lv_e; l++) {
+                uint32_t t[2];
+                tmem_ld2(tD + lane_base + 2 * l, t);
+                wait_ld();
+                const uint32_t gp = pack_f16x2(__uint_as_float(t[0]), __uint_as_float(t[1]));
+                const __half2 g = *reinterpret_cast<const __half2*>(&gp);
+                GridLevel c;
+                grid_level_cell(a.enc, l, x0, x1, x2, c);
+                __half2* base = gg + a.enc.level_offset[l];
+#pragma unroll
+                for (int k = 0; k < 8; k++) red_add_f16x2(base + c.idx[k], __hmul2(__half2half2(__float2half_rn(c.w[k])), g));
+            }
+            // (every thread's reads of tD are complete -- wait::ld -- before it reaches the next tile's first barrier)
+        }
+    }
+    NRC_PROF(8);
+    if (weights_pending) { cp_async_wait_all(); mbar_arrive(&wbar); }
+#pragma unroll
+    for (int b = 0; b < 2; b++)
+        if (pend[b]) { mbar_wait(&bar_dw[b], ph_dw[b]); ph_dw[b] ^= 1; pend[b] = false; }
+    fence_after();
+
+    // ---------------- weight-gradient partial of this CTA.  M = 64 accumulators: row 16 * q + i (i < 16) of D lives in TMEM lane 32 * q + i
+    if (it > 0) {
+        float* out = a.dw_partials + (size_t)blockIdx.x * a.n_mlp;
+        const int drow = quad * 16 + lane;
+        for (int m = 0; m <= H; m++) {
+            const int bw = m == 0 ? IN_W : m < H ? kWidth : kOutPad;
+            const uint32_t tW = m == 0 ? tW0 : m < H ? tWh + (uint32_t)(m - 1) * 64 : tWo;
+            const size_t moff = m == 0 ? 0 : (size_t)IN_W * kWidth + (size_t)(m - 1) * kWidth * kWidth;
+            for (int c = part * 16; c < bw; c += 16 * TPR) {
+                uint32_t v[16];
+                tmem_ld16(tW + lane_base + c, v);
+                wait_ld();
+                if (lane < 16) {
+                    if (m < H) {
+                        float4* dst = reinterpret_cast<float4*>(out + moff + (size_t)drow * bw + c);
+#pragma unroll
+                        for (int q = 0; q < 4; q++) dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                    } else {      // output layer accumulated transposed: D[in][out] -> W_out[out][in]
+#pragma unroll
+                        for (int q = 0; q < 16; q++) out[moff + (size_t)(c + q) * kWidth + drow] = __uint_as_float(v[q]);
+                    }
+                }
+            }
+        }
+    }
+    NRC_PROF(9);
+    // ---------------- Trainer::loss (trainer.h:205-207): the CTA that finishes last adds the tile partials in tile order
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(a.done_counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (s_last && warp == 0) {
+        __threadfence();
+        float s = 0;
+        for (uint32_t i0 = 0; i0 < n_tiles; i0 += 32) {
+            const float v = (i0 + lane < n_tiles) ? __ldcg(a.loss_partials + i0 + lane) : 0.0f;
+#pragma unroll
+            for (int j = 0; j < 32; j++) { const float vj = __shfl_sync(0xffffffffu, v, j); if (i0 + j < n_tiles) s += vj; }
+        }
+        if (lane == 0) { *a.loss_out = s; *a.done_counter = 0u; }
+    }
+    fence_before();
+    __syncthreads();
+    NRC_PROF(10);
+    timeline_end(a.tl, 0);
+    if (warp == 0) tmem_dealloc(tmem_base_s, 512);
+}
+
+// fp32 sum of the per-CTA weight-gradient partials, fixed order (deterministic): a CTA owns 64 parameters, four thread groups
+// add a quarter of the chunks each, the four partial sums are added in group order
+__global__ void __launch_bounds__(256) nrc_reduce_partials_kernel(const float* __restrict__ partials, uint32_t n_chunks, uint32_t n_mlp, float* __restrict__ out,
+                                                                  unsigned long long* tl = nullptr) {
+    __shared__ float s[4][64];
+    timeline_begin(tl, 0);
+    const uint32_t pl = threadIdx.x & 63, slice = threadIdx.x >> 6, i = blockIdx.x * 64 + pl;
+    const uint32_t per = (n_chunks + 3) / 4, c0 = slice * per, c1 = min(n_chunks, c0 + per);
     float g = 0;
-    for (uint32_t c = 0; c < n_chunks; c++) g += partials[(size_t)c * n_mlp + i];
-    out[i] = g;
+    if (i < n_mlp) {
+#pragma unroll 8
+        for (uint32_t c = c0; c < c1; c++) g += partials[(size_t)c * n_mlp + i];
+    }
+    s[slice][pl] = g;
+    __syncthreads();
+    if (slice == 0 && i < n_mlp) out[i] = ((s[0][pl] + s[1][pl]) + s[2][pl]) + s[3][pl];
+    timeline_end(tl, 0);
 }
 
 // materialise the fp16 MLP gradient (what tcnn keeps in Trainer::param_gradients) without running the optimizer
@@ -1360,7 +1764,10 @@ struct OptArgs {
     __half* grad16;
     const float* partials;
     uint32_t n_chunks;
+    uint32_t mlp_blocks;        // nrc_adam_kernel: CTAs [0, mlp_blocks) own 64 network weights each
     float lr, beta1, beta2, eps, l2_reg, loss_scale, ema_decay, ema_debias_old, ema_debias_new, log2_beta1, log2_beta2;
+    unsigned long long* tl;     // optional device-side timeline slots (development aid)
+    unsigned long long* tl_ema;
 };
 
 // adam.h:48-121 for one parameter whose state is already in registers; returns the new fp32 master weight
@@ -1375,120 +1782,123 @@ __device__ __forceinline__ float adam_update(const OptArgs& a, float wfp, float&
     return wfp - eff * m1;
 }
 
-// adam.h:48-121 followed by ema.h:63-76 in one pass over the parameter vector.  Eight consecutive parameters per thread
-// (128-bit accesses to the fp16 vectors; gradient, weights and EMA are requested up front).  Encoding entries whose gradient
-// is zero skip Adam (adam.h:77-80); the touched ones are few and scattered, so each warp first compacts them (ballot + popc
-// ranks into a shared list) and then runs Adam densely, one touched ENTRY (two features, one 32-byte state sector) per lane,
-// instead of executing mostly-predicated-off copies of the update.  The new fp16 weights travel back to their owner thread
-// through shared memory, so weights, EMA and the re-zeroed gradient are written with full 128-bit stores.
-// Two instantiations, two launches: MLP = true covers the network weights (dense Adam, 12 CTAs), MLP = false the hash-grid entries.
-// The encoding instance is latency-bound on its dependent loads (gradient -> ballot -> per-entry state): ncu showed 43 % of DRAM
-// peak at 3 CTAs/SM with the combined 77-register kernel; without the network branch it fits 6 CTAs/SM (measured: the training
-// step 155 -> 145 us).
+// The optimizer runs as two kernels (adam.h:48-121, ema.h:63-76):
+//   nrc_adam_kernel      ONE launch on the training stream: the first n_mlp / 64 CTAs own 64 network weights each (fixed-order sum of
+//                        the per-CTA weight-gradient partials, dense Adam, EMA); the remaining CTAs run Adam on the hash-grid entries
+//                        whose gradient is non-zero (adam.h:77-80) -- the only part of the optimizer the NEXT training step depends on
+//                        (it reads the fp16 working weights).  (Round 2 measured the network part as its own kernels on a side
+//                        stream: they were only dispatched once every CTA of the encoding grid had been, 25 us on the critical path.)
+//   nrc_grid_ema_kernel  hash-grid entries: dense EMA of the fp16 weights (what Inference() reads); nothing in a training step reads
+//                        it, so it runs on a side stream underneath the next step's forward / backward kernel: a persistent grid of one
+//                        small CTA per SM that fits next to that kernel's CTA.
+// The touched hash-grid entries are few (a quarter at the reference's batch size) and scattered, so each warp first compacts them
+// (ballot + popc ranks into a shared list) and then runs Adam densely, one touched ENTRY (two features, one 32-byte state sector) per
+// lane, instead of executing mostly-predicated-off copies of the update.  The new fp16 weights are written entry by entry; nothing
+// else of the fp16 weight vector is read.  Consumed gradients are re-zeroed here, so the next step needs no 28.5 MB memset.
 #ifndef NRC_OPT_MIN_BLOCKS
 #define NRC_OPT_MIN_BLOCKS 6
 #endif
-template <bool MLP>
-__global__ void __launch_bounds__(256, MLP ? 1 : NRC_OPT_MIN_BLOCKS) nrc_optimizer_kernel(const __grid_constant__ OptArgs a) {
-    __shared__ uint32_t s_g[8][128];       // per warp: compacted gradients (half2 bits) of the touched entries ...
+__global__ void __launch_bounds__(256, NRC_OPT_MIN_BLOCKS) nrc_adam_kernel(const __grid_constant__ OptArgs a) {
+    __shared__ uint32_t s_g[8][128];       // per warp: compacted gradients (half2 bits) of the touched entries ... (network CTAs: partial sums)
     __shared__ uint16_t s_el[8][128];      // ... and their entry index inside the warp's 128-entry span
-    __shared__ uint32_t s_w[8][128];       // new fp16 weights (half2 bits) by rank
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // n_mlp is a multiple of 1024 (64-wide layers, 16-aligned inputs): the network instance covers [0, n_mlp), the encoding
-    // instance starts at n_mlp; a warp (256 parameters) never straddles the boundary
-    const uint64_t base = MLP ? 0 : a.n_mlp;
-    const uint64_t i0 = base + ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 8;
-    const uint64_t warp_i0 = base + ((uint64_t)blockIdx.x * 256 + warp * 32) * 8;
-    if (warp_i0 >= (MLP ? a.n_mlp : a.n_params)) return;     // whole warp out of range
-    const bool in_range = i0 < a.n_params;
-    constexpr bool is_mlp = MLP;
-    union V8 { int4 v; __half h[8]; uint32_t u[4]; };
-    V8 g, w, e;
-    g.v = make_int4(0, 0, 0, 0); w.v = g.v; e.v = g.v;
     const float inv_scale = 1.0f / a.loss_scale;
-    if (in_range) e.v = *reinterpret_cast<const int4*>(a.ema16 + i0);
-    if (is_mlp) {
-        // network weights: every parameter is updated; gradient = fixed-order sum of the weight-gradient partials
-        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (uint32_t c = 0; c < a.n_chunks; c++) {
-            const float4* p = reinterpret_cast<const float4*>(a.partials + (size_t)c * a.n_mlp + i0);
-            const float4 p0 = p[0], p1 = p[1];
-            acc[0] += p0.x; acc[1] += p0.y; acc[2] += p0.z; acc[3] += p0.w; acc[4] += p1.x; acc[5] += p1.y; acc[6] += p1.z; acc[7] += p1.w;
+    timeline_begin(a.tl, 0);
+    if (blockIdx.x < a.mlp_blocks) {
+        // ---- network weights: 64 per CTA; four thread groups add a quarter of the partials each, in chunk order (deterministic)
+        float* s = reinterpret_cast<float*>(&s_g[0][0]);          // [4][64]
+        const uint32_t pl = threadIdx.x & 63, slice = threadIdx.x >> 6, i = blockIdx.x * 64 + pl;
+        const uint32_t per = (a.n_chunks + 3) / 4, c0 = slice * per, c1 = min(a.n_chunks, c0 + per);
+        float gsum = 0;
+#pragma unroll 8
+        for (uint32_t c = c0; c < c1; c++) gsum += a.partials[(size_t)c * a.n_mlp + i];
+        s[slice * 64 + pl] = gsum;
+        __syncthreads();
+        if (slice == 0) {
+            const float acc = ((s[pl] + s[64 + pl]) + s[128 + pl]) + s[192 + pl];
+            const __half g16 = __float2half_rn(acc);                       // tcnn keeps gradients in fp16 (trainer.h:322-336)
+            float mw = a.master[i], m1 = a.m1[i], m2 = a.m2[i];
+            uint32_t st = a.steps[i];
+            const float gradient = __half2float(g16) * inv_scale + a.l2_reg * mw;
+            mw = adam_update(a, mw, m1, m2, st, gradient);
+            const __half w = __float2half_rn(mw);
+            a.master[i] = mw; a.m1[i] = m1; a.m2[i] = m2; a.steps[i] = st;
+            a.grad16[i] = g16; a.w16[i] = w;
+            const float filtered = (__half2float(a.ema16[i]) * a.ema_decay * a.ema_debias_old + __half2float(w) * (1 - a.ema_decay)) * a.ema_debias_new;
+            a.ema16[i] = __float2half_rn(filtered);
         }
-        float mw[8], m1[8], m2[8]; uint32_t st[8];
-        *reinterpret_cast<float4*>(mw) = *reinterpret_cast<const float4*>(a.master + i0); *reinterpret_cast<float4*>(mw + 4) = *reinterpret_cast<const float4*>(a.master + i0 + 4);
-        *reinterpret_cast<float4*>(m1) = *reinterpret_cast<const float4*>(a.m1 + i0); *reinterpret_cast<float4*>(m1 + 4) = *reinterpret_cast<const float4*>(a.m1 + i0 + 4);
-        *reinterpret_cast<float4*>(m2) = *reinterpret_cast<const float4*>(a.m2 + i0); *reinterpret_cast<float4*>(m2 + 4) = *reinterpret_cast<const float4*>(a.m2 + i0 + 4);
-        *reinterpret_cast<uint4*>(st) = *reinterpret_cast<const uint4*>(a.steps + i0); *reinterpret_cast<uint4*>(st + 4) = *reinterpret_cast<const uint4*>(a.steps + i0 + 4);
+        return;
+    }
+    const uint32_t gb = blockIdx.x - a.mlp_blocks;
+    const uint64_t i0 = a.n_mlp + ((uint64_t)gb * 256 + threadIdx.x) * 8;
+    const uint64_t warp_i0 = a.n_mlp + ((uint64_t)gb * 256 + warp * 32) * 8;
+    if (warp_i0 >= a.n_params) return;     // whole warp out of range
+    union V8 { int4 v; uint32_t u[4]; };
+    V8 g;
+    g.v = make_int4(0, 0, 0, 0);
+    if (i0 < a.n_params) g.v = *reinterpret_cast<const int4*>(a.grad16 + i0);
+    uint32_t base = 0, my_rank[4];
+    bool mine[4];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            g.h[j] = __float2half_rn(acc[j]);                              // tcnn keeps gradients in fp16 (trainer.h:322-336)
-            const float gradient = __half2float(g.h[j]) * inv_scale + a.l2_reg * mw[j];
-            mw[j] = adam_update(a, mw[j], m1[j], m2[j], st[j], gradient);
-            w.h[j] = __float2half_rn(mw[j]);
-        }
-        *reinterpret_cast<float4*>(a.master + i0) = *reinterpret_cast<float4*>(mw); *reinterpret_cast<float4*>(a.master + i0 + 4) = *reinterpret_cast<float4*>(mw + 4);
-        *reinterpret_cast<float4*>(a.m1 + i0) = *reinterpret_cast<float4*>(m1); *reinterpret_cast<float4*>(a.m1 + i0 + 4) = *reinterpret_cast<float4*>(m1 + 4);
-        *reinterpret_cast<float4*>(a.m2 + i0) = *reinterpret_cast<float4*>(m2); *reinterpret_cast<float4*>(a.m2 + i0 + 4) = *reinterpret_cast<float4*>(m2 + 4);
-        *reinterpret_cast<uint4*>(a.steps + i0) = *reinterpret_cast<uint4*>(st); *reinterpret_cast<uint4*>(a.steps + i0 + 4) = *reinterpret_cast<uint4*>(st + 4);
-        *reinterpret_cast<int4*>(a.grad16 + i0) = g.v;
-        *reinterpret_cast<int4*>(a.w16 + i0) = w.v;
-    } else {
-        if (in_range) { g.v = *reinterpret_cast<const int4*>(a.grad16 + i0); w.v = *reinterpret_cast<const int4*>(a.w16 + i0); }
-        uint32_t base = 0, my_rank[4];
-        bool mine[4];
+    for (int j = 0; j < 4; j++) {
+        mine[j] = (g.u[j] & 0x7fff7fffu) != 0u;              // at least one of the entry's two gradients is non-zero (+-0 both skip)
+        const uint32_t b = __ballot_sync(0xffffffffu, mine[j]);
+        my_rank[j] = base + __popc(b & ((1u << lane) - 1));
+        base += __popc(b);
+    }
+    if (base) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            mine[j] = (g.u[j] & 0x7fff7fffu) != 0u;              // at least one of the entry's two gradients is non-zero (+-0 both skip)
-            const uint32_t b = __ballot_sync(0xffffffffu, mine[j]);
-            my_rank[j] = base + __popc(b & ((1u << lane) - 1));
-            base += __popc(b);
-        }
-        if (base) {
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (mine[j]) { s_el[warp][my_rank[j]] = (uint16_t)(lane * 4 + j); s_g[warp][my_rank[j]] = g.u[j]; }
-            __syncwarp();
-            GridAdamState* st0 = a.grid_state + ((warp_i0 - a.n_mlp) >> 1);
-            for (uint32_t r = lane; r < base; r += 32) {
-                float4* sp = reinterpret_cast<float4*>(st0 + s_el[warp][r]);
-                float4 s0 = sp[0];                                  // master.xy, m1.xy
-                float4 s1 = sp[1];                                  // m2.xy, steps.xy
-                const uint32_t gb = s_g[warp][r];
-                const __half2 gh = *reinterpret_cast<const __half2*>(&gb);
-                const float g0 = __low2float(gh), g1 = __high2float(gh);
-                uint32_t t0 = __float_as_uint(s1.z), t1 = __float_as_uint(s1.w);
-                if (g0 != 0.0f) s0.x = adam_update(a, s0.x, s0.z, s1.x, t0, g0 * inv_scale);
-                if (g1 != 0.0f) s0.y = adam_update(a, s0.y, s0.w, s1.y, t1, g1 * inv_scale);
-                s1.z = __uint_as_float(t0); s1.w = __uint_as_float(t1);
-                sp[0] = s0; sp[1] = s1;
-                s_w[warp][r] = tc05::pack_f16x2(s0.x, s0.y);
-            }
-            __syncwarp();
-            bool any = false;
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (mine[j]) {
-                    // a feature whose own gradient is zero keeps its fp16 weight bit for bit (its master did not move)
-                    const uint32_t nw = s_w[warp][my_rank[j]];
-                    const uint32_t keep_lo = (g.u[j] & 0x00007fffu) ? 0u : 0x0000ffffu, keep_hi = (g.u[j] & 0x7fff0000u) ? 0u : 0xffff0000u;
-                    const uint32_t keep = keep_lo | keep_hi;
-                    w.u[j] = (w.u[j] & keep) | (nw & ~keep);
-                    any = true;
-                }
-            if (any) {
-                *reinterpret_cast<int4*>(a.w16 + i0) = w.v;
-                *reinterpret_cast<int4*>(a.grad16 + i0) = make_int4(0, 0, 0, 0);   // consumed
-            }
+        for (int j = 0; j < 4; j++)
+            if (mine[j]) { s_el[warp][my_rank[j]] = (uint16_t)(lane * 4 + j); s_g[warp][my_rank[j]] = g.u[j]; }
+        if (mine[0] | mine[1] | mine[2] | mine[3]) *reinterpret_cast<int4*>(a.grad16 + i0) = make_int4(0, 0, 0, 0);   // consumed
+        __syncwarp();
+        GridAdamState* st0 = a.grid_state + ((warp_i0 - a.n_mlp) >> 1);          // first entry of the warp's span
+        uint32_t* w0 = reinterpret_cast<uint32_t*>(a.w16 + warp_i0);
+        for (uint32_t r = lane; r < base; r += 32) {
+            const uint32_t el = s_el[warp][r];
+            float4* sp = reinterpret_cast<float4*>(st0 + el);
+            float4 s0 = sp[0];                                  // master.xy, m1.xy
+            float4 s1 = sp[1];                                  // m2.xy, steps.xy
+            const uint32_t gbits = s_g[warp][r];
+            const __half2 gh = *reinterpret_cast<const __half2*>(&gbits);
+            const float g0 = __low2float(gh), g1 = __high2float(gh);
+            uint32_t t0 = __float_as_uint(s1.z), t1 = __float_as_uint(s1.w);
+            if (g0 != 0.0f) s0.x = adam_update(a, s0.x, s0.z, s1.x, t0, g0 * inv_scale);
+            if (g1 != 0.0f) s0.y = adam_update(a, s0.y, s0.w, s1.y, t1, g1 * inv_scale);
+            s1.z = __uint_as_float(t0); s1.w = __uint_as_float(t1);
+            sp[0] = s0; sp[1] = s1;
+            // fp16 working weights of the entry; a feature whose own gradient is zero keeps its master weight, hence its fp16 bits
+            w0[el] = tc05::pack_f16x2(s0.x, s0.y);
         }
     }
-    if (!in_range) return;
+    timeline_end(a.tl, 0);
+}
+
+// dense EMA of the hash-grid part of the fp16 weight vector (ema.h:63-76): persistent grid-stride loop, four 16-byte vectors of each
+// array in flight per thread
+__global__ void __launch_bounds__(256) nrc_grid_ema_kernel(const __grid_constant__ OptArgs a) {
+    const uint64_t n_vec = (a.n_params - a.n_mlp) / 8, stride = (uint64_t)gridDim.x * 256;
+    int4* wv = reinterpret_cast<int4*>(a.w16 + a.n_mlp);
+    int4* ev = reinterpret_cast<int4*>(a.ema16 + a.n_mlp);
+    timeline_begin(a.tl_ema, 0);
+    for (uint64_t v0 = (uint64_t)blockIdx.x * 256 + threadIdx.x; v0 < n_vec; v0 += 4 * stride) {
+        union V8 { int4 v; __half h[8]; };
+        V8 w[4], e[4];
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const float filtered = (__half2float(e.h[j]) * a.ema_decay * a.ema_debias_old + __half2float(w.h[j]) * (1 - a.ema_decay)) * a.ema_debias_new;
-        e.h[j] = __float2half_rn(filtered);
+        for (int u = 0; u < 4; u++) {
+            const uint64_t v = v0 + u * stride;
+            if (v < n_vec) { w[u].v = wv[v]; e[u].v = ev[v]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint64_t v = v0 + u * stride;
+            if (v >= n_vec) break;
+#pragma unroll
+            for (int j = 0; j < 8; j++) e[u].h[j] = __float2half_rn((__half2float(e[u].h[j]) * a.ema_decay * a.ema_debias_old + __half2float(w[u].h[j]) * (1 - a.ema_decay)) * a.ema_debias_new);
+            ev[v] = e[u].v;
+        }
     }
-    *reinterpret_cast<int4*>(a.ema16 + i0) = e.v;
+    timeline_end(a.tl_ema, 0);
 }
 
 // (un)packing between the tcnn parameter order and the per-entry Adam records (nrc_get_params / nrc_set_params_fp32)

@@ -11,5 +11,5 @@ rng = np.random.default_rng(1)
 c = NeuralRadianceCache(AppConfig.default())
 d_in = [torch.from_numpy(synth_records(rng, n)).cuda() for _ in range(4)]
 d_tgt = [torch.from_numpy((rng.random((n, 3), dtype=np.float32) * 2).astype(np.float32)).cuda() for _ in range(4)]
-for i in range(8): c.training_step(d_in[i % 4], d_tgt[i % 4], n, True)
+for i in range(24): c.training_step(d_in[i % 4], d_tgt[i % 4], n, True)
 torch.cuda.synchronize()

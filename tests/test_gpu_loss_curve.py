@@ -65,3 +65,43 @@ def test_loss_curve_1000_steps_vs_tcnn(name):
     e_theirs = np.linalg.norm(theirs - truth) / np.linalg.norm(truth)
     assert e_ours <= 1.15 * e_theirs + 0.01, (e_ours, e_theirs)   # as good a fit as the reference's
     assert np.linalg.norm(ours - theirs) / np.linalg.norm(theirs) <= 2.0 * max(e_ours, e_theirs) + 0.01
+
+
+@pytest.mark.parametrize("name,max_ln,mean_ln", [("hash_ob_d6", 0.05, 0.01), ("tri_ob_d5", 0.10, 0.03)])
+def test_loss_curve_mean_over_data_orders_vs_tcnn(name, max_ln, mean_ln):
+    """loss curves within 5 % per 50-step window.  A single trajectory cannot be held to that (docstring above: two
+    faithful restatements differ by more), but the EXPECTED curve can: tests/golden/tcnn_loss1000_<cfg>_seeds.npz holds the
+    reference's own tiny-cuda-nn curves for six data orders (make_tcnn_loss_curve.py seeds, recorded on a B200); the CUDA path
+    trains on the same six orders and the window means, averaged over the orders, are compared.  Measured (round 2, B200):
+    hash_ob_d6 (the reference default) max |ln| 0.030, mean 0.003 -> bound 5 %, the contract; tri_ob_d5 (no encoding parameters,
+    the loss falls 180x) max 0.074, mean 0.018, while tcnn's own order-to-order spread of a window mean is sigma(ln) = 0.3 there,
+    i.e. a standard error of 0.12 for six orders -> bound 10 %."""
+    import torch
+    from nrc_hpm_renderer_b200 import AppConfig
+    from nrc_hpm_renderer_b200.nrc import NeuralRadianceCache
+    path = os.path.join(ROOT, "tests", "golden", f"tcnn_loss1000_{name}_seeds.npz")
+    if not os.path.exists(path):
+        pytest.skip("fixture not recorded yet")
+    z = np.load(path)
+    B, steps = int(z["batch"]), int(z["steps"])
+    ours = []
+    for seed in z["seeds"]:
+        tin, tgt, _ = _generator().training_data(int(seed), B, steps)
+        app = AppConfig.default()
+        app.pos_enc_id, app.dir_enc_id, app.nn_depth, app.learning_rate = int(z["pos"]), int(z["dir"]), int(z["depth"]), float(z["lr"])
+        c = NeuralRadianceCache(app)
+        d_in, d_tgt = torch.from_numpy(tin).cuda(), torch.from_numpy(tgt).cuda()
+        losses = np.empty(steps, np.float32)
+        for s in range(steps):
+            c.training_step(d_in[s * B:(s + 1) * B], d_tgt[s * B:(s + 1) * B], B, True)
+            losses[s] = c.GetLoss()
+        ours.append(losses)
+        c.Destroy()
+    ours, ref = np.stack(ours), z["losses"]
+    assert np.all(np.isfinite(ours))
+    assert np.max(np.abs(ours[:, 0] - ref[:, 0]) / ref[:, 0]) <= 1e-3          # identical weights and records: same first loss, every order
+    w = 50
+    om = ours.reshape(len(ours), -1, w).mean(2).mean(0); tm = ref.reshape(len(ref), -1, w).mean(2).mean(0)
+    ln = np.log(om / tm)
+    print(f"{name}: mean over {len(ours)} data orders, per-window ln(loss/loss_tcnn): max {np.abs(ln).max():.3f} mean {np.abs(ln).mean():.3f}")
+    assert np.abs(ln).max() <= max_ln and np.abs(ln).mean() <= mean_ln, (np.abs(ln).max(), np.abs(ln).mean())
