@@ -318,6 +318,7 @@ void NrcCache::setup_kernels() {
         NRCHPM_CUDA(cudaFuncSetAttribute(nrc_forward2_kernel<IN_W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd2_smem_bytes<IN_W>(H, 3)));
         NRCHPM_CUDA(cudaFuncSetAttribute(nrc_forward2_kernel<IN_W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd2_smem_bytes<IN_W>(H, 1)));
         NRCHPM_CUDA(cudaFuncSetAttribute(nrc_backward2_kernel<IN_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd2_smem_bytes<IN_W>(H)));
+        NRCHPM_CUDA(cudaFuncSetAttribute(nrc_infer_ws_kernel<IN_W, NRC_WS_NP, NRC_WS_NC, ws_slots(IN_W)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)infer_ws_smem_bytes<IN_W>(H, ws_slots(IN_W))));
         if (fused_training_fits()) {
             NRCHPM_CUDA(cudaFuncSetAttribute(nrc_train_fused_kernel<IN_W, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train_smem_bytes<IN_W>(H)));
             NRCHPM_CUDA(cudaFuncSetAttribute(nrc_train_fused_kernel<IN_W, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train_smem_bytes<IN_W>(H)));
@@ -326,6 +327,7 @@ void NrcCache::setup_kernels() {
     // tuning knobs (experiments only; the defaults are the measured best)
     if (const char* v = std::getenv("NRCHPM_INFER_GROUPS")) infer_groups_ = std::max(0, std::min(3, std::atoi(v)));
     if (const char* v = std::getenv("NRCHPM_TRAIN_GROUPS")) train_groups_ = std::max(0, std::min(1, std::atoi(v)));
+    if (const char* v = std::getenv("NRCHPM_INFER_WS")) infer_ws_ = std::atoi(v) != 0 ? 1 : 0;   // 0: tile-per-warpgroup kernel
     if (const char* v = std::getenv("NRCHPM_TRAIN_FUSED")) train_fused_ = std::atoi(v) != 0;          // 0: the three-kernel path
     if (const char* v = std::getenv("NRCHPM_TRAIN_TPR")) train_tpr_ = std::atoi(v) == 4 ? 4 : 2;      // threads per record of the fused kernel
     if (const char* v = std::getenv("NRCHPM_TRAIN_PROF")) if (std::atoi(v)) { train_prof_.allocate((size_t)sm_count_ * 16); train_prof_.zero(); timeline_.allocate(2 * kTimelineSlots); reset_timeline(); }   // development aid
@@ -387,6 +389,13 @@ void NrcCache::inference(const float* d_in, float* d_out, uint32_t n, bool use_e
             nrc_forward2_kernel<IN_W, false><<<grid, g * kGroupThreads, fwd2_smem_bytes<IN_W>(cfg_.n_hidden_layers, (int)g), s>>>(a);
         });
         check_launch("nrc_forward2_kernel<infer>");
+        return;
+    }
+    if (infer_ws_ > 0 && enc_.pos_enc == POS_HASHGRID && infer_max_ctas_ == 0 && tiles >= (uint32_t)sm_count_) {
+        // warp-specialised persistent kernel: one CTA per SM, producer warpgroups encode, consumer warpgroups run the MLP
+        grid = (uint32_t)sm_count_;
+        NRC_DISPATCH_INW(enc_.in_w, { nrc_infer_ws_kernel<IN_W, NRC_WS_NP, NRC_WS_NC, ws_slots(IN_W)><<<grid, (NRC_WS_NP + NRC_WS_NC) * 128, infer_ws_smem_bytes<IN_W>(cfg_.n_hidden_layers, ws_slots(IN_W)), s>>>(a); });
+        check_launch("nrc_infer_ws_kernel");
         return;
     }
     // persistent grid: kInferWgs warpgroups (tiles in flight) per CTA, kInferCtas CTAs per SM; small batches use fewer warpgroups

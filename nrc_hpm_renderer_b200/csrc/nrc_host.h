@@ -104,6 +104,7 @@ private:
     float loss_host_ = 0;
     cudaStream_t train_stream_last_ = nullptr;       // stream of the last training step: loss(), gradient_buffers() order themselves behind it
     bool train_fused_ = true; int train_tpr_ = 2;
+    int infer_ws_ = 1;                               // warp-specialised inference kernel (0: tile-per-warpgroup kernel)
     DeviceBuffer<unsigned int> train_done_;
     DeviceBuffer<long long> train_prof_;
     DeviceBuffer<unsigned long long> timeline_;

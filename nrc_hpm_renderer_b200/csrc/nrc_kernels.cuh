@@ -311,7 +311,6 @@ __device__ __forceinline__ void hashgrid_run_simple(const EncParams& e, const __
 
 template <int KIND, class Put>
 __device__ __forceinline__ void hashgrid_run(const EncParams& e, const __half2* __restrict__ grid, float x0, float x1, float x2, int lb, int le, Put& put) {
-    if (NRC_GATHER_PIPE == 2) { hashgrid_run_simple<KIND>(e, grid, x0, x1, x2, lb, le, put); return; }
     LevelLoads A, B;
     level_issue<KIND>(e, grid, lb, x0, x1, x2, A);
     for (int l = lb; l < le; l += 2) {
@@ -333,9 +332,15 @@ __device__ __forceinline__ void hashgrid_pipelined(const EncParams& e, const __h
         const uint32_t kind = e.level_kind[l];
         int r = l + 1;
         while (r < l_end && e.level_kind[r] == kind) r++;
-        if (kind == 2) hashgrid_run<2>(e, grid, x0, x1, x2, l, r, put);
-        else if (kind == 1) hashgrid_run<1>(e, grid, x0, x1, x2, l, r, put);
-        else hashgrid_run<0>(e, grid, x0, x1, x2, l, r, put);
+        if (NRC_GATHER_PIPE == 2) {
+            if (kind == 2) hashgrid_run_simple<2>(e, grid, x0, x1, x2, l, r, put);
+            else if (kind == 1) hashgrid_run_simple<1>(e, grid, x0, x1, x2, l, r, put);
+            else hashgrid_run_simple<0>(e, grid, x0, x1, x2, l, r, put);
+        } else {
+            if (kind == 2) hashgrid_run<2>(e, grid, x0, x1, x2, l, r, put);
+            else if (kind == 1) hashgrid_run<1>(e, grid, x0, x1, x2, l, r, put);
+            else hashgrid_run<0>(e, grid, x0, x1, x2, l, r, put);
+        }
         l = r;
     }
 }
@@ -728,6 +733,206 @@ __global__ void __launch_bounds__(TRAIN ? kFwdThreads : kInferWgs * 128, TRAIN ?
             if (lane == 0) loss_red[wg][warp & 3] = loss;
             named_bar_sync(1 + wg, 128);
             if (r == 0) a.loss_partials[tile] = ((loss_red[wg][0] + loss_red[wg][1]) + loss_red[wg][2]) + loss_red[wg][3];
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base_s, kAlloc);
+}
+
+// ---------------------------------------------------------------------------------------------- warp-specialised inference
+// Round-2 inference kernel.  nrc_forward_kernel<.., false> gives every warpgroup a whole tile: 16 rounds of hash-grid gathers, then
+// seven dependent tcgen05 layers; ncu (profiles/r01_ncu_fwd_infer_final.txt) showed the launch taking the SUM of the two phases
+// (0.38 ms of gathers + 0.26 ms of MLP) because tensor memory caps the resident tiles at four per SM.  Here the two phases run in
+// different warps of one persistent CTA per SM:
+//   * NP producer warpgroups (no tensor memory, no accumulator registers): one record per thread, hash-grid gathers with the index
+//     arithmetic specialised per level kind (dense / hashed / wrapped), OneBlob, -> a ring of NS K-major X tiles in shared memory;
+//     `full[slot]` (128 arrivals) hands a tile over;
+//   * NC consumer warpgroups: layer 0 straight from the ring slot (tcgen05.mma SS; its tcgen05.commit on `empty[slot]` returns the
+//     slot as soon as the tensor core has read it), layers 1..H and the output layer as before (TS mode, activations stay in TMEM).
+// The L1 -> L2 request path (the unit the gathers saturate, one 32-byte sector per request) is now fed continuously instead of in
+// bursts between MLP phases.  Measured on B200, 2 073 600 random records, HashGrid16x2 + OneBlob4, 64 x 6 (profiles/r02_summary.md):
+// tile-per-warpgroup kernel 0.633 ms; 4 producers + 2 consumers, 8 ring slots 0.576; 5 slots 0.562; 4 slots 0.539; 4 + 1, 4 slots
+// 0.534 (default); 3 + 1, 3 slots 0.537; 5 + 1 0.566; 6 + 2 (64 registers, spills) 0.592; pipelined gathers: no change -- the fewer
+// ring slots, the larger the L1 that serves the second corner of an x-edge, and 12 producer warps already saturate the request path.
+// One consumer warpgroup sustains 0.36 ms per frame, enough next to the gathers but not for encodings without table look-ups:
+// those keep the tile-per-warpgroup kernel (0.25 ms).
+template <class Put>
+__device__ __forceinline__ void hashgrid_by_kind(const EncParams& e, const __half2* __restrict__ grid, float x0, float x1, float x2, Put& put) {
+    int l = 0;
+    while (l < e.n_levels) {
+        const uint32_t kind = e.level_kind[l];
+        int r = l + 1;
+        while (r < e.n_levels && e.level_kind[r] == kind) r++;
+        if (kind == 2) hashgrid_run_simple<2>(e, grid, x0, x1, x2, l, r, put);
+        else if (kind == 1) hashgrid_run_simple<1>(e, grid, x0, x1, x2, l, r, put);
+        else hashgrid_run_simple<0>(e, grid, x0, x1, x2, l, r, put);
+        l = r;
+    }
+}
+
+// shape of the warp-specialised inference CTA (compile-time experiment knobs; defaults = measured best): producer / consumer
+// warpgroups, ring slots for encoded widths up to 48 (wider tiles get proportionally fewer), pipelined gathers in the producers
+#ifndef NRC_WS_NP
+#define NRC_WS_NP 4
+#endif
+#ifndef NRC_WS_NC
+#define NRC_WS_NC 1
+#endif
+#ifndef NRC_WS_SLOTS
+#define NRC_WS_SLOTS 4
+#endif
+#ifndef NRC_WS_PIPE
+#define NRC_WS_PIPE 0
+#endif
+#ifndef NRC_WS_STREAM
+#define NRC_WS_STREAM 1
+#endif
+#if NRC_WS_STREAM
+#define NRC_WS_LDCS(p) __ldcs(p)
+#else
+#define NRC_WS_LDCS(p) (*(p))
+#endif
+__host__ __device__ constexpr int ws_slots(int in_w) { return in_w <= 48 ? NRC_WS_SLOTS : (NRC_WS_SLOTS * 48) / in_w; }
+
+template <int IN_W>
+__host__ __device__ constexpr size_t infer_ws_smem_bytes(int n_hidden, int slots) {
+    return (size_t)IN_W * 128 + (size_t)(n_hidden - 1) * 8192 + 2048 + (size_t)slots * IN_W * 256;
+}
+
+template <int IN_W, int NP, int NC, int NS>
+__global__ void __launch_bounds__((NP + NC) * 128, 1) nrc_infer_ws_kernel(const __grid_constant__ FwdArgs a) {
+    using namespace tc05;
+    constexpr uint32_t kAlloc = NC <= 1 ? 128u : NC == 2 ? 256u : 512u;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t full[NS], empty[NS], mbar[NC];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, r = tid & 127;
+    const int H = a.n_hidden;
+    uint8_t* w0_s = smem;
+    uint8_t* wh_s = w0_s + IN_W * 128;
+    uint8_t* wo_s = wh_s + (H - 1) * 8192;
+    uint8_t* ring = wo_s + 2048;
+
+    if (warp == 0) { tmem_alloc(&tmem_base_s, kAlloc); tmem_relinquish(); }
+    if (tid == 0) {
+        for (int s = 0; s < NS; s++) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+        for (int c = 0; c < NC; c++) mbar_init(&mbar[c], 1);
+        fence_mbar_init();
+    }
+    copy_weights_kmajor(w0_s, a.params, kWidth, IN_W, tid, (NP + NC) * 128);
+    for (int l = 1; l < H; l++) copy_weights_kmajor(wh_s + (l - 1) * 8192, a.params + IN_W * kWidth + (l - 1) * kWidth * kWidth, kWidth, kWidth, tid, (NP + NC) * 128);
+    copy_weights_kmajor(wo_s, a.params + IN_W * kWidth + (H - 1) * kWidth * kWidth, kOutPad, kWidth, tid, (NP + NC) * 128);
+    fence_proxy_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+
+    uint32_t n = a.n;
+    if (a.d_count) n = min(n, *a.d_count);
+    const uint32_t n_tiles = (n + kTile - 1) / kTile;
+    const uint32_t n_my = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;      // tiles blockIdx.x + k * gridDim.x
+
+    if (wg < NP) {
+        // ------------------------------------------------------------ producers: records -> encoded X tiles
+        const __half2* grid = reinterpret_cast<const __half2*>(a.params + a.n_mlp);
+        const bool by_kind = a.enc.pos_enc == POS_HASHGRID && a.enc.all_pow2;
+        for (uint32_t k = wg; k < n_my; k += NP) {
+            const uint32_t slot = k % NS, use = k / NS;
+            const uint32_t row = (blockIdx.x + k * gridDim.x) * kTile + r;
+            float x0 = 0, x1 = 0, x2 = 0, th = 0, ph = 0;
+            if (row < n) {
+                const uint32_t rec = a.indices ? a.indices[row] : row;
+                const float* p = a.in + 5 * (size_t)rec;
+                // streaming loads: the records are read once and must not displace the hash-table lines from L1
+                x0 = NRC_WS_LDCS(p); x1 = NRC_WS_LDCS(p + 1); x2 = NRC_WS_LDCS(p + 2); th = NRC_WS_LDCS(p + 3); ph = NRC_WS_LDCS(p + 4);
+            }
+            if (use > 0) mbar_wait(&empty[slot], (use - 1) & 1);          // the tensor core has read the tile that lived here
+            SmemRowPut put{ring + slot * (IN_W * 256) + (r >> 3) * (IN_W * 16) + (r & 7) * 16};
+            if (by_kind) { hashgrid_by_kind(a.enc, grid, x0, x1, x2, put); encode_direction_pad(a.enc, th, ph, put); }
+            else encode_record<1>(a.enc, grid, x0, x1, x2, th, ph, put);
+            fence_proxy_async_smem();
+            mbar_arrive(&full[slot]);
+        }
+    } else {
+        // ------------------------------------------------------------ consumers: the MLP
+        const int c = wg - NP;
+        const uint32_t tD = tmem_base_s + c * 128, tA = tD + 64;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t idesc64 = make_idesc_f16(128, 64), idesc16 = make_idesc_f16(128, 16);
+        const uint32_t ring_addr = smem_u32(ring), w0_addr = smem_u32(w0_s), wh_addr = smem_u32(wh_s), wo_addr = smem_u32(wo_s);
+        uint64_t* bar = &mbar[c];
+        uint32_t phase = 0;
+        for (uint32_t k = c; k < n_my; k += NC) {
+            const uint32_t slot = k % NS, use = k / NS;
+            const uint32_t row = (blockIdx.x + k * gridDim.x) * kTile + r;
+            const bool valid = row < n;
+            uint32_t rec = 0;
+            if (valid) rec = a.indices ? a.indices[row] : row;
+            mbar_wait(&full[slot], use & 1);
+            if (r == 0) {
+                fence_after();
+                const uint32_t x_addr = ring_addr + slot * (IN_W * 256);
+#pragma unroll
+                for (int s = 0; s < IN_W / 16; s++)
+                    mma_f16_ss(tD, make_smem_desc(x_addr + s * 256, 128, IN_W * 16), make_smem_desc(w0_addr + s * 256, 128, IN_W * 16), idesc64, s > 0);
+                mma_commit(&empty[slot]);
+                mma_commit(bar);
+            }
+            mbar_wait(bar, phase); phase ^= 1;
+            fence_after();
+            for (int l = 0; l < H; l++) {
+#pragma unroll
+                for (int hf = 0; hf < 2; hf++) {
+                    uint32_t acc[32], p[16];
+                    tmem_ld32(tD + lane_base + hf * 32, acc);
+                    wait_ld();
+                    if (l == 0) {      // tcnn's ReLU is max(x, 0) in fp16: NaN (Q5) -> 0; cvt.relu would keep it
+                        const __half2 zero2 = __float2half2_rn(0.0f);
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            uint32_t v = pack_f16x2(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
+                            __half2 m = __hmax2(*reinterpret_cast<__half2*>(&v), zero2);
+                            p[j] = *reinterpret_cast<uint32_t*>(&m);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) p[j] = pack_relu_f16x2(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
+                    }
+                    tmem_st16(tA + lane_base + hf * 16, p);
+                }
+                wait_st();
+                fence_before();
+                named_bar_sync(1 + c, 128);
+                if (r == 0) {
+                    fence_after();
+                    if (l < H - 1) {
+#pragma unroll
+                        for (int s = 0; s < 4; s++) mma_f16_ts(tD, tA + s * 8, make_smem_desc(wh_addr + l * 8192 + s * 256, 128, 1024), idesc64, s > 0);
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < 4; s++) mma_f16_ts(tD, tA + s * 8, make_smem_desc(wo_addr + s * 256, 128, 1024), idesc16, s > 0);
+                    }
+                    mma_commit(bar);
+                }
+                mbar_wait(bar, phase); phase ^= 1;
+                fence_after();
+            }
+            // output layer: fp16 like tcnn's network output, then float (common_device.h:990-999)
+            uint32_t o[4];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]) : "r"(tD + lane_base) : "memory");
+            wait_ld();
+            if (valid) {
+                float* dst = a.out + 3 * (size_t)rec;
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    const float v = __half2float(__float2half_rn(__uint_as_float(o[q])));
+                    if (NRC_WS_STREAM) __stcs(dst + q, v); else dst[q] = v;
+                }
+            }
+            // (every thread's read of tD is complete -- wait::ld -- before the group's next barrier, which precedes the next MMA into tD ...
+            fence_before();
+            named_bar_sync(1 + c, 128);      // ... but the NEXT tile's layer-0 MMA is issued by thread 0 right after its wait on `full`: order it here)
         }
     }
     fence_before();
