@@ -19,6 +19,24 @@ std::atomic<uint64_t> g_launch_count{0};
 static thread_local std::string t_last_error;
 void set_last_error(const std::string& msg) { t_last_error = msg; }
 
+// launch of a training-path kernel with the access-policy window that keeps [grad16 | w16] in the persisting part of L2
+template <class K, class A>
+void NrcCache::launch_hot(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t s, const A& args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    if (l2_window_bytes_) {
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = hot_.ptr;
+        attr[0].val.accessPolicyWindow.num_bytes = l2_window_bytes_;
+        attr[0].val.accessPolicyWindow.hitRatio = l2_hit_ratio_;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+    }
+    NRCHPM_CUDA(cudaLaunchKernelEx(&cfg, kernel, args));
+}
+
 // ------------------------------------------------------------------------------------------------ config
 static int parse_pos(const mini_json::Value& v, NrcConfig& c) {
     const std::string t = v.string("otype", "");
@@ -203,7 +221,7 @@ void NrcCache::init_params(uint64_t seed) {
         for (int field = 1; field <= 3; field++) scatter_grid_field(field, zeros.ptr);
         NRCHPM_CUDA(cudaDeviceSynchronize());
     }
-    NRCHPM_CUDA(cudaMemset(grad16_.ptr, 0, grad16_.bytes()));
+    NRCHPM_CUDA(cudaMemset(hot_.ptr, 0, grad16_.bytes()));
     current_step_ = 0;
 }
 
@@ -215,7 +233,22 @@ NrcCache::NrcCache(const NrcConfig& cfg, uint64_t seed) : cfg_(cfg) {
     NRCHPM_CUDA(cudaGetDeviceProperties(&prop, dev));
     if (prop.major != 10) throw Error(NRCHPM_ERR_CUDA, std::string("this library contains sm_100a code only; device is ") + prop.name);
     sm_count_ = prop.multiProcessorCount;
-    w16_.allocate(n_params_); ema16_.allocate(n_params_); grad16_.allocate(n_params_);
+    {
+        const size_t n_pad = (n_params_ + 63) / 64 * 64;
+        hot_.allocate(2 * n_pad);
+        grad16_.ptr = hot_.ptr; grad16_.count = n_params_;               // first: the cudaIpc handle of the gradient is the allocation's
+        w16_.ptr = hot_.ptr + n_pad; w16_.count = n_params_;
+        ema16_.allocate(n_params_);
+        const char* v = std::getenv("NRCHPM_L2_PERSIST");
+        if (n_grid_ && !(v && std::atoi(v) == 0) && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+            const size_t want = std::min<size_t>(hot_.bytes(), (size_t)prop.accessPolicyMaxWindowSize);
+            const size_t aside = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, want);
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, aside) == cudaSuccess) {
+                l2_window_bytes_ = want;
+                l2_hit_ratio_ = (float)std::min(1.0, (double)aside / (double)want);
+            } else cudaGetLastError();
+        }
+    }
     master_.allocate(n_mlp_); m1_.allocate(n_mlp_); m2_.allocate(n_mlp_); steps_.allocate(n_mlp_);      // network weights: SoA
     grid_state_.allocate(n_grid_ / 2);                                                                    // encoding: one record per entry
     loss_dev_.allocate(1);
@@ -453,8 +486,8 @@ void NrcCache::training_step(const float* d_in, const float* d_target, uint32_t 
         a.prof = train_prof_.ptr;
         a.tl = timeline_slot();
         const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t)sm_count_);
-        if (train_tpr_ == 4) { NRC_DISPATCH_INW(enc_.in_w, { nrc_train_fused_kernel<IN_W, 4><<<grid, 512, train_smem_bytes<IN_W>(H), s>>>(a); }); }
-        else { NRC_DISPATCH_INW(enc_.in_w, { nrc_train_fused_kernel<IN_W, 2><<<grid, 256, train_smem_bytes<IN_W>(H), s>>>(a); }); }
+        if (train_tpr_ == 4) { NRC_DISPATCH_INW(enc_.in_w, { launch_hot(nrc_train_fused_kernel<IN_W, 4>, grid, 512, train_smem_bytes<IN_W>(H), s, a); }); }
+        else { NRC_DISPATCH_INW(enc_.in_w, { launch_hot(nrc_train_fused_kernel<IN_W, 2>, grid, 256, train_smem_bytes<IN_W>(H), s, a); }); }
         check_launch("nrc_train_fused_kernel");
         dw_chunks_ = grid;
         grid_grad_dirty_ = n_grid_ != 0;
@@ -548,13 +581,13 @@ void NrcCache::optimizer_step(cudaStream_t s) {
     if (ema_in_flight_) NRCHPM_CUDA(cudaStreamWaitEvent(s, ema_done_, 0));        // the previous step's EMA pass still reads the weights
     a.mlp_blocks = (uint32_t)(n_mlp_ / 64);
     const unsigned grid_blocks = has_grid ? (unsigned)(((n_params_ - n_mlp_) / 8 + 255) / 256) : 0u;
-    nrc_adam_kernel<<<a.mlp_blocks + grid_blocks, 256, 0, s>>>(a);
+    launch_hot(nrc_adam_kernel, a.mlp_blocks + grid_blocks, 256, 0, s, a);
     check_launch("nrc_adam_kernel");
     if (has_grid) {
         // ---- the dense EMA of the hash-grid weights, which only Inference() reads: side stream, underneath the next step
         NRCHPM_CUDA(cudaEventRecord(adam_done_, s));
         NRCHPM_CUDA(cudaStreamWaitEvent(ema_stream_, adam_done_, 0));
-        nrc_grid_ema_kernel<<<(unsigned)sm_count_, 256, 0, ema_stream_>>>(a);
+        launch_hot(nrc_grid_ema_kernel, (unsigned)sm_count_, 256, 0, ema_stream_, a);
         check_launch("nrc_grid_ema_kernel");
         NRCHPM_CUDA(cudaEventRecord(ema_done_, ema_stream_));
         ema_in_flight_ = true;

@@ -2003,6 +2003,9 @@ __device__ __forceinline__ float adam_update(const OptArgs& a, float wfp, float&
 #ifndef NRC_OPT_MIN_BLOCKS
 #define NRC_OPT_MIN_BLOCKS 6
 #endif
+#ifndef NRC_OPT_STREAM_STATE
+#define NRC_OPT_STREAM_STATE 0
+#endif
 __global__ void __launch_bounds__(256, NRC_OPT_MIN_BLOCKS) nrc_adam_kernel(const __grid_constant__ OptArgs a) {
     __shared__ uint32_t s_g[8][128];       // per warp: compacted gradients (half2 bits) of the touched entries ... (network CTAs: partial sums)
     __shared__ uint16_t s_el[8][128];      // ... and their entry index inside the warp's 128-entry span
@@ -2062,8 +2065,13 @@ __global__ void __launch_bounds__(256, NRC_OPT_MIN_BLOCKS) nrc_adam_kernel(const
         for (uint32_t r = lane; r < base; r += 32) {
             const uint32_t el = s_el[warp][r];
             float4* sp = reinterpret_cast<float4*>(st0 + el);
+#if NRC_OPT_STREAM_STATE
+            float4 s0 = __ldcs(sp);                             // master.xy, m1.xy   (evict-first: the state streams through L2 once per step)
+            float4 s1 = __ldcs(sp + 1);                         // m2.xy, steps.xy
+#else
             float4 s0 = sp[0];                                  // master.xy, m1.xy
             float4 s1 = sp[1];                                  // m2.xy, steps.xy
+#endif
             const uint32_t gbits = s_g[warp][r];
             const __half2 gh = *reinterpret_cast<const __half2*>(&gbits);
             const float g0 = __low2float(gh), g1 = __high2float(gh);
@@ -2071,7 +2079,11 @@ __global__ void __launch_bounds__(256, NRC_OPT_MIN_BLOCKS) nrc_adam_kernel(const
             if (g0 != 0.0f) s0.x = adam_update(a, s0.x, s0.z, s1.x, t0, g0 * inv_scale);
             if (g1 != 0.0f) s0.y = adam_update(a, s0.y, s0.w, s1.y, t1, g1 * inv_scale);
             s1.z = __uint_as_float(t0); s1.w = __uint_as_float(t1);
+#if NRC_OPT_STREAM_STATE
+            __stcs(sp, s0); __stcs(sp + 1, s1);
+#else
             sp[0] = s0; sp[1] = s1;
+#endif
             // fp16 working weights of the entry; a feature whose own gradient is zero keeps its master weight, hence its fp16 bits
             w0[el] = tc05::pack_f16x2(s0.x, s0.y);
         }
