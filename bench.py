@@ -7,11 +7,14 @@ Workload (BASELINE.json configs[1]): one 1920x1080 frame of the reference's defa
 (`RelativeL2Luminance Adam 0.01 0.99 0 0 64 6 21 14 4 ...`, reference src/main.cu:432-439): HashGrid16x2 + OneBlob4
 encoding, 64 x 6 fully fused MLP.  One "step" is NeuralRadianceCache::InferAndTrain for that frame (reference
 src/NeuralRadianceCache.cu:97-156): inference on W*H = 2 073 600 query records + 4 training steps of 2^14 records.
-`value` = queries (inference + training records) per second, whole job, inputs resident in HBM.
-`e2e`   = the same step through the host-buffer C-ABI entry points (pinned host memory, H2D + D2H inside the timed region).
-`frame` = the full frame loop on the bundled cloud (tracking + NRC + compositing) with per-stage milliseconds.
-N > 1 (torchrun): weak scaling -- every rank owns one 1080p screen tile (its own query records and training records),
-weights are replicated and the gradients of every training step are averaged with an NCCL all-reduce over NVLink.
+`value` = queries (inference + training records) per second, whole job, inputs resident in HBM, through the reference-level
+          entry points of the C ABI (nrc_init + nrc_inference + nrc_train; nrc_infer_and_train for N > 1).
+`e2e`   = the same step through nrc_infer_and_train_host (pinned host memory, H2D + D2H inside the timed region).
+`frame` = the full frame loop on the bundled cloud (tracking + NRC + compositing) with per-stage milliseconds, for BASELINE
+          configs 2 (scene 0, 1080p), 4 (dense medium, long paths, 1080p) and 1 (256x256).
+N > 1 (torchrun): weak scaling -- every rank owns one 1080p screen tile (its own query and training records); weights are
+replicated and the gradients of every training step are summed over NVLink by the library's own peer-memory kernel; the library
+(C++) overlaps the frame's inference with the exchanges (NrcCache::infer_and_train_overlapped).
 
 --impl reference times the reference's own implementation of the step: tiny-cuda-nn built unmodified for sm_100a
 (oracle/_ref/tcnn_oracle, driven exactly like en::NeuralRadianceCache); if that binary is absent, the scalar CPU oracle.
@@ -19,6 +22,7 @@ weights are replicated and the gradients of every training step are averaged wit
 from __future__ import annotations
 
 import argparse
+import glob
 import json
 import os
 import subprocess
@@ -39,7 +43,14 @@ SKY_HALF = np.array([62.317, 42.295, 76.707], np.float32) / 2
 METRIC, UNIT = "nrc_queries_per_s_1080p_infer_and_train", "queries/s"
 FLOP_PER_QUERY_H6 = 2 * (48 * 64 + 5 * 64 * 64 + 64 * 3)        # 47 488 (H = 6)
 BYTES_PER_QUERY = 20 + 12 + 16 * 8 * 4                            # record in + radiance out + hash-grid gathers = 544 B
-NCU_DRAM_BYTES_PER_LAUNCH = 70_055_168 + 11_916_032               # ncu capture of the inference launch (profiles/, round 1)
+# identical in both arms (the driver compares the strings)
+WORKLOAD = ("NeuralRadianceCache::InferAndTrain, one 1920x1080 frame per GPU: 2073600 inference records + 4x16384 training records, "
+            "HashGrid16x2+OneBlob4, MLP 64x6 (reference default argv)")
+
+
+def base_config(world=1):
+    return {"workload": WORKLOAD, "records": "synthetic, seed 1337", "l2": f"{N_SETS} record sets rotated (265 MB > 126 MB L2)",
+            "parallelism": f"tiles x{world}, data-parallel training" if world > 1 else "single GPU"}
 
 
 def synth_records(rng, n):
@@ -94,14 +105,23 @@ def peaks():
     return {"hbm_gbs": 6650.0, "tflops": 1590.0, "tflops_sustained": 1400.0, "which": "fallback"}
 
 
+def ncu_extract():
+    """newest committed ncu extract of the dominant kernel (profiles/r??_dominant_kernel_ncu.json, written by scripts/ncu_extract.py)"""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_dominant_kernel_ncu.json")))
+    if not files:
+        return None
+    j = json.load(open(files[-1]))
+    j["file"] = os.path.relpath(files[-1], ROOT)
+    return j
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     binp = os.path.join(ROOT, "oracle", "_ref", "tcnn_oracle")
-    cfg = {"workload": "NeuralRadianceCache::InferAndTrain, one 1920x1080 frame: 2073600 inference records + 4x16384 training records, "
-                       "HashGrid16x2+OneBlob4, MLP 64x6 (reference default argv)", "records": "synthetic, seed 1337", "l2": f"{N_SETS} record sets rotated (> L2)"}
+    cfg = base_config(int(os.environ.get("WORLD_SIZE", "1")))       # the same config object as our arm prints at this N (rank 0 alone runs the reference)
     if os.path.exists(binp):
         cmd = [binp, "bench", f"n_infer={N_INFER}", f"batch={TRAIN_BATCH}", f"batches={TRAIN_BATCHES}", f"frames={args.steps}", f"warmup={max(args.warmup, 3)}",
                "pos=0", "dir=0", "depth=6", f"sets={N_SETS}"]
@@ -143,42 +163,75 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def quarter_cloud():
+    from nrc_hpm_renderer_b200 import volume
+    path = os.path.join(ROOT, "data", "wdas_cloud_quarter_u8.npz")
+    if os.path.exists(path):
+        return volume.load_volume(path).data, "wdas_cloud_quarter (498x338x613 u8, bundled cloud)"
+    small = np.load(os.path.join(ROOT, "tests", "golden", "wdas_cloud_sixteenth_u8.npz"))["data"]
+    return np.ascontiguousarray(small.repeat(4, 0).repeat(4, 1).repeat(4, 2)), "wdas_cloud_sixteenth upsampled x4 (quarter fixture missing)"
+
+
 def cpu_baseline_leg():
+    """north_star: "a scalar CPU implementation of the same MLP and tracker timed on the box's host cores in the same run, with the core
+    count stated".  NRC: the oracle (OpenMP over records) on one full frame of inference records + one 2^14 training step.  Tracker:
+    the oracle's gen_rays + prep_infer + prep_train (OpenMP over pixels) on the bundled cloud at config 1 (256x256) and config 2 (1080p)."""
     import oracle as O
+    from nrc_hpm_renderer_b200 import Camera, HpmSceneConfig, calc_train_subset, sky_size
+    from nrc_hpm_renderer_b200.renderer import dir_light_vec
     O.build()
+    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
     o = O.NrcOracle(O.nrc_config(0, 0, 6))
     rng = np.random.default_rng(1337)
-    n_i, n_t = N_INFER, TRAIN_BATCH            # one full frame of inference records + one 2^14 training step (~10-20 s of host time)
+    n_i, n_t = N_INFER, TRAIN_BATCH
     rec, tin, tgt = synth_records(rng, n_i), synth_records(rng, n_t), (rng.random((n_t, 3), dtype=np.float32) * 2).astype(np.float32)
     t0 = time.perf_counter()
     o.inference(rec)
+    t_inf = time.perf_counter() - t0
     o.training_step(tin, tgt)
-    t = time.perf_counter() - t0
-    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
-    return {"value": (n_i + n_t) / t, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"oracle/nrc_oracle.cpp (OpenMP, {cores} threads): {n_i} inference records + one {n_t}-record training step, {t:.1f} s"}
+    t_nrc = time.perf_counter() - t0
+    grid, _ = quarter_cloud()
+    d, h, w = grid.shape
+    sc = HpmSceneConfig.preset(0)
+    osc = O.make_scene(grid, sky_size((w, h, d)), sc.density, 0.8, dir_light_vec(-1.57, 0.0), sc.dir_light_strength)
+    fr = np.array([0.3, 0.6, 0.9, 0.2], np.float32)
+    tracker = {}
+    for name, (tw, th, T) in (("config1_256x256", (256, 256, 1 << 14)), ("config2_1920x1080", (W, H, 1 << 16))):
+        ts = calc_train_subset(tw, th, T)
+        cfg = O.make_config(tw, th, ts.train_width, ts.train_height, ts.x_dist, ts.x_dist, 1, 1, 0.0, T, 1, 1 << 21)
+        cam = Camera(aspect=tw / th)
+        ocam = O.make_camera(cam.inv_proj_view, cam.pos)
+        t1 = time.perf_counter()
+        r = O.gen_rays(osc, cfg, ocam, fr)
+        O.prep_infer(osc, cfg, r)
+        _, _, l2 = O.prep_train(osc, cfg, r, fr, O.new_ring(cfg))
+        t_tr = time.perf_counter() - t1
+        tracker[name] = {"ms": round(t_tr * 1e3, 2), "density_lookups": int(r["lookups"] + l2), "lookups_per_s": (r["lookups"] + l2) / t_tr}
+    # config 1 as written: one tracking pass at 256x256 + inference on its 65 536 records + one training step
+    t_c1 = tracker["config1_256x256"]["ms"] * 1e-3 + t_inf * 65536 / n_i + (t_nrc - t_inf)
+    return {"value": (n_i + n_t) / t_nrc, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"oracle/nrc_oracle.cpp (OpenMP, {cores} threads): {n_i} inference records + one {n_t}-record training step, {t_nrc:.1f} s; "
+                      f"oracle/hpm_oracle.cpp tracker passes on the bundled cloud (same threads)",
+            "tracker": tracker, "config1_frame_ms": round(t_c1 * 1e3, 1)}
 
 
 def frame_leg(torch, stream, steps, warmup):
     """full frame loop on the bundled cloud: tracking + NRC + compositing (per-stage ms, density-lookup roofline)"""
-    from nrc_hpm_renderer_b200 import AppConfig, Camera, HpmSceneConfig, volume
+    from nrc_hpm_renderer_b200 import AppConfig, Camera, HpmSceneConfig
     from nrc_hpm_renderer_b200.nrc import NeuralRadianceCache
     from nrc_hpm_renderer_b200.renderer import BUF_COUNTERS, HpmScene, NrcHpmRenderer
-    path = os.path.join(ROOT, "data", "wdas_cloud_quarter_u8.npz")
-    if os.path.exists(path):
-        grid, vol_name = volume.load_volume(path).data, "wdas_cloud_quarter (498x338x613 u8, bundled cloud)"
-    else:
-        small = np.load(os.path.join(ROOT, "tests", "golden", "wdas_cloud_sixteenth_u8.npz"))["data"]
-        grid, vol_name = np.ascontiguousarray(small.repeat(4, 0).repeat(4, 1).repeat(4, 2)), "wdas_cloud_sixteenth upsampled x4 (quarter fixture missing)"
-    app = AppConfig.default()
-    app.scene = HpmSceneConfig.preset(0)
-    out = {"volume": vol_name, "scene": 0}
-    for mode, compact, pipelined in (("compact", True, False), ("all_records", False, False), ("compact_pipelined_training", True, True)):
+    grid, vol_name = quarter_cloud()
+    out = {"volume": vol_name}
+
+    def run(w, h, scene_id, env, prl, prob, batches, compact=True, pipelined=False):
+        app = AppConfig.default()
+        app.scene = HpmSceneConfig.preset(scene_id)
+        app.primary_ray_length, app.primary_ray_prob, app.train_batch_count = prl, prob, batches
         nrc = NeuralRadianceCache(app)
-        scene = HpmScene(grid, app.scene)
+        scene = HpmScene(grid, app.scene, env_color=env)
         # pipelined: Train(N) runs underneath the tracking passes of frame N+1 (same order of effects); per-frame time = the main
         # stream from gen_rays to compositing, which includes waiting for the previous frame's training before Inference()
-        r = NrcHpmRenderer(W, H, False, Camera(aspect=W / H), app, scene, nrc, compact_inference=compact, pipeline_train=pipelined, stream=stream)
+        r = NrcHpmRenderer(w, h, False, Camera(aspect=w / h), app, scene, nrc, compact_inference=compact, pipeline_train=pipelined, stream=stream)
         rng = np.random.default_rng(1337)
         stages = []
         for i in range(warmup + steps):
@@ -187,14 +240,25 @@ def frame_leg(torch, stream, steps, warmup):
                 stages.append(r.EvaluateTimestampQueries())
         cnt = r.read(BUF_COUNTERS)
         ms = {k: float(np.mean([s[k] for s in stages])) for k in stages[0]}
-        out[mode] = {"ms": {k: round(v, 4) for k, v in ms.items()}, "frames_per_s": 1e3 / ms["total"], "density_lookups_gen_rays": int(cnt[0]),
-                     "density_lookups_prep_train": int(cnt[1]), "active_records": int(cnt[2]), "loss": nrc.GetLoss()}
-        if compact and not pipelined:
-            # tracking roofline: L lookups x 1 B + P pixels x 36 B, and the sector-granular figure L x 32 B
-            L, P = int(cnt[0]), W * H
-            t = ms["gen_rays"] * 1e-3
-            out["tracking_roofline"] = {"algorithmic_GBps": (L + 36 * P) / t / 1e9, "sector_GBps": (32 * L + 36 * P) / t / 1e9, "lookups_per_s": L / t}
+        res = {"ms": {k: round(v, 4) for k, v in ms.items()}, "frames_per_s": 1e3 / ms["total"], "density_lookups_gen_rays": int(cnt[0]),
+               "density_lookups_prep_train": int(cnt[1]), "active_records": int(cnt[2]), "loss": nrc.GetLoss()}
+        L, P = int(cnt[0]), w * h
+        t = ms["gen_rays"] * 1e-3
+        # tracking roofline: L lookups x 1 B + P pixels x 36 B, and the sector-granular figure L x 32 B
+        res["tracking_roofline"] = {"algorithmic_GBps": (L + 36 * P) / t / 1e9, "sector_GBps": (32 * L + 36 * P) / t / 1e9, "lookups_per_s": L / t}
         r.Destroy(); scene.Destroy(); nrc.Destroy()
+        return res
+
+    # BASELINE config 2: scene 0 at 1080p -- compacted inference (default), the reference's all-records mode, pipelined training
+    out["config2_scene0_1080p"] = {"compact": run(W, H, 0, (0, 0, 0), 1, 0.0, 4), "all_records": run(W, H, 0, (0, 0, 0), 1, 0.0, 4, compact=False),
+                                  "compact_pipelined_training": run(W, H, 0, (0, 0, 0), 1, 0.0, 4, pipelined=True)}
+    # BASELINE config 4: dense medium (scene-5 density 1.6), long paths (primaryRayLength 4, primaryRayProb .75)
+    out["config4_dense_long_paths_1080p"] = run(W, H, 5, (1, 1, 1), 4, 0.75, 4)
+    # BASELINE config 1: 256x256, one training step
+    out["config1_256x256"] = run(256, 256, 0, (0, 0, 0), 1, 0.0, 1)
+    ex = ncu_extract()
+    if ex and "gen_rays" in ex:
+        out["tracking_issue_roofline"] = ex["gen_rays"]      # the tracker is bound by instruction issue, not bytes: ncu issue-slot utilisation
     return out
 
 
@@ -202,15 +266,12 @@ def frame_tiles_leg(torch, dist, rank, world, steps, warmup):
     """BASELINE config 5: a 3840x2160 frame cut into `world` column strips (one per GPU), tracking + inference per strip without any
     exchange, cache training data-parallel (1/world of every batch per rank, gradients summed through peer memory).  ms per frame =
     max over ranks of the per-rank frame time (CUDA events)."""
-    from nrc_hpm_renderer_b200 import AppConfig, Camera, HpmSceneConfig, volume
+    from nrc_hpm_renderer_b200 import AppConfig, Camera, HpmSceneConfig
     from nrc_hpm_renderer_b200.nrc import NeuralRadianceCache
     from nrc_hpm_renderer_b200.parallel import PeerGradientExchange
     from nrc_hpm_renderer_b200.renderer import HpmScene, NrcHpmRenderer, make_tile_render_config, tile_app_config
     Wt, Ht = 3840, 2160
-    path = os.path.join(ROOT, "data", "wdas_cloud_quarter_u8.npz")
-    if not os.path.exists(path):
-        return {"error": "bundled volume fixture missing"}
-    grid = volume.load_volume(path).data
+    grid, vol_name = quarter_cloud()
     app = AppConfig.default(); app.scene = HpmSceneConfig.preset(0)
     ta = tile_app_config(app, world)
     nrc = NeuralRadianceCache(ta)
@@ -233,6 +294,37 @@ def frame_tiles_leg(torch, dist, rank, world, steps, warmup):
     return out
 
 
+def exchange_check(torch, dist, world, rank):
+    """correctness of the sharded data-parallel step over peer memory (nrc_peer_adam_kernel), carried in the bench line so that the
+    scaling run records it: after every step all ranks hold bit-identical fp16 working and EMA weights, every gradient buffer is clean
+    (consumed words cleared at their owners), and the loss falls.  (scripts/check_peer_exchange.py additionally pins the sum against
+    NCCL and the fused kernel against its step-by-step form, bit for bit; the GPU test suite runs it when two devices are present.)"""
+    from nrc_hpm_renderer_b200 import AppConfig, nrc as N
+    from nrc_hpm_renderer_b200.parallel import PeerGradientExchange
+    B = 4096
+    c = N.NeuralRadianceCache(AppConfig.default())
+    PeerGradientExchange(c, world)
+    rng = np.random.default_rng(100 + rank)
+    n_mlp = c.n_mlp_params
+    w0 = c.get_params(N.WORKING)
+    losses = []
+    for step in range(6):
+        rec = torch.from_numpy(synth_records(rng, B)).cuda(); tgt = torch.from_numpy((rng.random((B, 3), dtype=np.float32) * 2).astype(np.float32)).cuda()
+        c.training_step(rec, tgt, B, False); c.peer_exchange(); c.optimizer_step()
+        losses.append(c.GetLoss())
+    torch.cuda.synchronize(); dist.barrier()
+    w = torch.from_numpy(c.get_params(N.WORKING)).cuda(); e = torch.from_numpy(c.get_params(N.EMA)).cuda()
+    gw = [torch.empty_like(w) for _ in range(world)]; ge = [torch.empty_like(e) for _ in range(world)]
+    dist.all_gather(gw, w); dist.all_gather(ge, e)
+    f = torch.tensor([int(bool((c.get_params(N.GRAD)[n_mlp:] == 0).all())), int(bool(np.mean(w.cpu().numpy()[n_mlp:] != w0[n_mlp:]) > 0.1))], device="cuda")
+    dist.all_reduce(f, op=dist.ReduceOp.MIN)
+    res = {"replicas_bit_identical_after_6_steps": all(torch.equal(gw[0], t) for t in gw) and all(torch.equal(ge[0], t) for t in ge),
+           "gradient_buffers_clean": bool(f[0]), "weights_of_all_slices_updated": bool(f[1]), "loss_first_last": [losses[0], losses[-1]]}
+    res["ok"] = bool(res["replicas_bit_identical_after_6_steps"] and res["gradient_buffers_clean"] and res["weights_of_all_slices_updated"] and losses[-1] < losses[0])
+    c.Destroy()
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -246,7 +338,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from nrc_hpm_renderer_b200 import AppConfig, _lib
     from nrc_hpm_renderer_b200.nrc import NeuralRadianceCache
-    from nrc_hpm_renderer_b200.parallel import GradientAllReduce, OverlappedInferAndTrain, PeerGradientExchange, make_gradient_exchange
+    from nrc_hpm_renderer_b200.parallel import PeerGradientExchange, make_gradient_exchange
 
     app = AppConfig.default()                          # reference default argv: hash grid + OneBlob, 64 x 6, lr 0.01, EMA 0.99
     nrc = NeuralRadianceCache(app)
@@ -260,32 +352,28 @@ def run_ours(args):
     h_tgt = [(rng.random((n_train, 3), dtype=np.float32) * 2).astype(np.float32) for _ in range(N_SETS)]
     d_tin = [torch.from_numpy(a).cuda() for a in h_tin]
     d_tgt = [torch.from_numpy(a).cuda() for a in h_tgt]
-    overlap_default = 1 if world > 1 else 0          # measured at N = 2: 1.53 ms overlapped vs 1.61 ms serial (profiles/r01_summary.md)
-    # N > 1: the tile's inference runs underneath the gradient all-reduces (parallel.OverlappedInferAndTrain); N = 1 keeps the
-    # reference's serial Inference() -> Train() schedule unless --overlap asks for the same two-stream schedule
-    overlap = args.overlap if args.overlap is not None else overlap_default
-    runner = OverlappedInferAndTrain(nrc, world) if overlap else None
-    allreduce = make_gradient_exchange(nrc, world) if (world > 1 and runner is None) else None
+    exchange = make_gradient_exchange(nrc, world) if world > 1 else None
+    peer = isinstance(exchange, PeerGradientExchange)
 
-    def exchange_gradients():
-        if isinstance(allreduce, PeerGradientExchange):
-            allreduce.run(sp)
-        else:
-            allreduce.run()
+    def bind(s):
+        # en::NeuralRadianceCache::Init on this step's record set (the reference binds its Vulkan buffers once; rotating four sets keeps the inputs > L2)
+        nrc.Init(N_INFER, d_in[s], d_out[s], d_tin[s], d_tgt[s], None, None, sp)
 
-    def step(i):
+    def step(i, events=None):
         s = i % N_SETS
-        if runner is not None:
-            runner.run(d_in[s], d_out[s], N_INFER, d_tin[s], d_tgt[s], TRAIN_BATCH, TRAIN_BATCHES)
+        bind(s)
+        if world > 1 and peer:
+            nrc.InferAndTrain(None, True)              # the library picks the overlapped data-parallel schedule (C++)
             return
-        nrc.inference(d_in[s], d_out[s], N_INFER, True, sp)                      # Inference(): one batch (2^21 >= W*H), EMA weights
-        for b in range(TRAIN_BATCHES):                                           # Train(): 4 x training_step
-            tin = d_tin[s][b * TRAIN_BATCH:(b + 1) * TRAIN_BATCH]; tgt = d_tgt[s][b * TRAIN_BATCH:(b + 1) * TRAIN_BATCH]
-            if allreduce is None:
-                nrc.training_step(tin, tgt, TRAIN_BATCH, True, sp)
-            else:
-                nrc.training_step(tin, tgt, TRAIN_BATCH, False, sp)
-                exchange_gradients()
+        if events: events[0].record(stream)
+        nrc.Inference(None)                            # Inference(): one batch (2^21 >= W*H), EMA weights
+        if events: events[1].record(stream)
+        if world == 1:
+            nrc.Train()                                # Train(): 4 x training_step
+        else:                                          # NCCL fallback (no peer access between the devices): serial schedule
+            for b in range(TRAIN_BATCHES):
+                nrc.training_step(d_tin[s][b * TRAIN_BATCH:(b + 1) * TRAIN_BATCH], d_tgt[s][b * TRAIN_BATCH:(b + 1) * TRAIN_BATCH], TRAIN_BATCH, False, sp)
+                exchange.run()
                 nrc.optimizer_step(sp)
 
     def barrier():
@@ -305,28 +393,13 @@ def run_ours(args):
     ev_k = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0.record(stream)
     for i in range(args.steps):
-        s = (warmup + i) % N_SETS
-        if runner is not None:
-            step(warmup + i)
-            continue
-        # dominant kernel, timed live on its own stream: the fused encode + MLP inference launch
-        ev_k[i][0].record(stream)
-        nrc.inference(d_in[s], d_out[s], N_INFER, True, sp)
-        ev_k[i][1].record(stream)
-        for b in range(TRAIN_BATCHES):
-            tin = d_tin[s][b * TRAIN_BATCH:(b + 1) * TRAIN_BATCH]; tgt = d_tgt[s][b * TRAIN_BATCH:(b + 1) * TRAIN_BATCH]
-            if allreduce is None:
-                nrc.training_step(tin, tgt, TRAIN_BATCH, True, sp)
-            else:
-                nrc.training_step(tin, tgt, TRAIN_BATCH, False, sp)
-                exchange_gradients()
-                nrc.optimizer_step(sp)
+        step(warmup + i, ev_k[i])                      # dominant kernel, timed live on its own stream: the fused encode + MLP inference launch
     e1.record(stream)
     barrier()
     launches = _lib.lib().nrchpm_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
-    if runner is not None:
+    if world > 1 and peer:
         # the overlapped schedule has no serial inference launch to bracket: time the dominant kernel alone afterwards
         for i in range(args.steps):
             s = (warmup + i) % N_SETS
@@ -335,45 +408,37 @@ def run_ours(args):
             ev_k[i][1].record(stream)
         torch.cuda.synchronize()
     ms_kernel = float(np.mean([a.elapsed_time(b) for a, b in ev_k]))
-    # exposed cost of the gradient exchange: the same schedule with the all-reduce left out (replicas diverge; timing only)
-    exchange = None
-    if world > 1:
-        saved = runner.allreduce if runner is not None else None
-        if runner is not None:
-            runner.allreduce = None
-        barrier()
-        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n_x = max(3, min(args.steps, 50))
-        x0.record(stream)
-        for i in range(n_x):
-            if runner is not None:
-                step(i)
-            else:
-                s = i % N_SETS
-                nrc.inference(d_in[s], d_out[s], N_INFER, True, sp)
-                for b in range(TRAIN_BATCHES):
-                    nrc.training_step(d_tin[s][b * TRAIN_BATCH:(b + 1) * TRAIN_BATCH], d_tgt[s][b * TRAIN_BATCH:(b + 1) * TRAIN_BATCH], TRAIN_BATCH, True, sp)
-        x1.record(stream)
-        barrier()
-        ms_nocomm = x0.elapsed_time(x1) / n_x
-        if runner is not None:
-            runner.allreduce = saved
-        ar = runner.allreduce if runner is not None else allreduce
-        exchange = {"kind": "own kernel over peer memory (nrc_peer_reduce_kernel: P2P loads/stores over NVLink)" if isinstance(ar, PeerGradientExchange) else "NCCL all-reduce",
-                    "bytes_per_training_step": ar.bytes_per_step, "all_reduces_per_step": TRAIN_BATCHES, "ms_per_step_without_exchange": ms_nocomm,
-                    "schedule": "inference chunks overlap the all-reduces" if runner is not None else "serial"}
     if world > 1:
         t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
     ms_step = ms / args.steps
     q_step = (N_INFER + n_train) * world
     value = q_step / (ms_step * 1e-3)
 
+    # ---- exposed cost of the gradient exchange: the serial single-GPU schedule on an un-paired cache of this rank (no exchange)
+    exchange_info = None
+    if world > 1:
+        solo = NeuralRadianceCache(app)
+        n_x = max(3, min(args.steps, 50))
+        for i in range(3 + n_x):
+            if i == 3:
+                barrier(); x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True); x0.record(stream)
+            s = i % N_SETS
+            solo.Init(N_INFER, d_in[s], d_out[s], d_tin[s], d_tgt[s], None, None, sp)
+            solo.InferAndTrain(None, True)
+        x1.record(stream); barrier()
+        ms_solo = x0.elapsed_time(x1) / n_x
+        solo.Destroy()
+        check = exchange_check(torch, dist, world, rank) if peer else None
+        exchange_info = {"kind": "own kernel over NVLink peer memory (nrc_peer_adam_kernel): reduce-scatter of the gradient slice, Adam on the slice, all-gather of the fp16 weights, pipelined span by span" if peer else "NCCL all-reduce",
+                         "bytes_per_training_step": exchange.bytes_per_step, "exchanges_per_step": TRAIN_BATCHES,
+                         "ms_per_step_single_gpu_schedule_without_exchange": ms_solo, "exposed_ms_per_step": ms_step - ms_solo,
+                         "schedule": "nrc_infer_and_train: Inference() then Train(), each training step = forward/backward kernel + one peer kernel" if peer else "serial", "check": check}
+
     # ---- e2e: host buffers through the C ABI (pinned memory), H2D + D2H every step
     pin_in = [torch.from_numpy(synth_records(rng, N_INFER)).pin_memory() for _ in range(2)]
     pin_out = torch.empty((N_INFER, 3), dtype=torch.float32).pin_memory()
     pin_tin = [torch.from_numpy(h_tin[i]).pin_memory() for i in range(2)]
     pin_tgt = [torch.from_numpy(h_tgt[i]).pin_memory() for i in range(2)]
-
     np_in, np_out = [t.numpy() for t in pin_in], pin_out.numpy()
     np_tin, np_tgt = [t.numpy() for t in pin_tin], [t.numpy() for t in pin_tgt]
 
@@ -395,6 +460,21 @@ def run_ours(args):
     e2e_value = q_step / (e2e_ms / e2e_steps * 1e-3)
     h2d = N_INFER * 20 + n_train * 32
     d2h = N_INFER * 12 + 4 * TRAIN_BATCHES
+    # transfer floor: the step's H2D and D2H copies alone, both directions at once, on every rank simultaneously (the host side of a
+    # multi-GPU box is shared: its memory bandwidth bounds the e2e number at N = 8)
+    dev_in = torch.empty((N_INFER + n_train * 2, 5), dtype=torch.float32, device="cuda")
+    s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(10):
+        with torch.cuda.stream(s_h2d):
+            dev_in[:N_INFER].copy_(pin_in[i % 2], non_blocking=True)
+        with torch.cuda.stream(s_d2h):
+            pin_out.copy_(d_out[i % N_SETS], non_blocking=True)
+    torch.cuda.synchronize()
+    xfer_ms = (time.perf_counter() - t0) * 1e2
+    if world > 1:
+        t = torch.tensor([xfer_ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); xfer_ms = float(t.item())
 
     frame_tiles = None
     if world > 1 and not args.no_frame:
@@ -404,27 +484,25 @@ def run_ours(args):
             frame_tiles = {"error": str(e)[:300]}
     if rank == 0:
         pk = peaks()
+        ex = ncu_extract()
         achieved_gbs = BYTES_PER_QUERY * N_INFER / (ms_kernel * 1e-3) / 1e9
         achieved_tf = FLOP_PER_QUERY_H6 * N_INFER / (ms_kernel * 1e-3) / 1e12
+        cfg = base_config(world)
+        schedule = "Inference() then Train(), serial (reference order)"
+        roof = {"kernel": "nrc_infer_ws_kernel<48,4,1,4> (hash-grid/OneBlob encode in 4 producer warpgroups -> smem ring -> 7-layer tcgen05 MLP in 1 consumer warpgroup + fp32 output)",
+                "bound": "hbm", "achieved": achieved_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / pk["hbm_gbs"],
+                "traffic": (ex or {}).get("dram_bytes_per_launch"), "traffic_source": (ex or {}).get("file"),
+                "note": "algorithmic bytes = 544 B/query (SURVEY.md 8d), 512 B of them hash-grid gathers that are served by L2 (tables are L2-resident), so DRAM "
+                        "traffic is far BELOW the algorithmic figure; the unit this kernel saturates is the L1->L2 request path (one 32-byte sector per gather request)",
+                "l2": (ex or {}).get("l2"), "peak_source": pk["which"], "ms_per_launch": ms_kernel, "algorithmic_bytes_per_query": BYTES_PER_QUERY,
+                "tensor": {"achieved_tflops": achieved_tf, "peak_tflops": pk["tflops_sustained"], "frac": achieved_tf / pk["tflops_sustained"], "flop_per_query": FLOP_PER_QUERY_H6}}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-               "config": {"workload": "NeuralRadianceCache::InferAndTrain, one 1920x1080 frame per GPU: 2073600 inference records + 4x16384 training records, "
-                                      "HashGrid16x2+OneBlob4, MLP 64x6 (reference default argv)", "records": "synthetic, seed 1337", "l2": f"{N_SETS} record sets rotated (265 MB > 126 MB L2)",
-                          "parallelism": f"tiles x{world}, data-parallel training" if world > 1 else "single GPU"},
-               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps},
-               "gpu_launches": int(launches), "clocks": clocks,
-               "roofline": {"kernel": "nrc_forward_kernel<48,false> (fused hash-grid/OneBlob encode + 7-layer tcgen05 MLP + fp32 output)", "bound": "hbm",
-                            "achieved": achieved_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / pk["hbm_gbs"], "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch (profiles/r01_ncu_fwd_infer_one_level_per_round.txt): "
-                                              "the 28.5 MB hash tables are L2-resident, DRAM sees the record I/O (66.4 MB) only",
-                            "l2": {"sectors_per_query": 57.2, "l1_to_l2_request_unit_busy": 0.66, "lts_throughput": 0.49, "note": "ncu, same capture: the unit this kernel loads most is the L1->L2 request path (one 32-byte sector per request, divergent gathers)"},
-                            "peak_source": pk["which"], "ms_per_launch": ms_kernel, "algorithmic_bytes_per_query": BYTES_PER_QUERY,
-                            "tensor": {"achieved_tflops": achieved_tf, "peak_tflops": pk["tflops_sustained"], "frac": achieved_tf / pk["tflops_sustained"], "flop_per_query": FLOP_PER_QUERY_H6}},
-               "loss": nrc.GetLoss()}
-        out["config"]["schedule"] = "inference overlapped with training (snapshot of the pre-training parameters)" if runner is not None else "Inference() then Train(), serial (reference order)"
-        if exchange is not None:
-            exchange["exposed_ms_per_step"] = ms_step - exchange["ms_per_step_without_exchange"]
-            out["gradient_exchange"] = exchange
+               "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": cfg, "schedule": schedule,
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps,
+                       "transfer_floor_ms": xfer_ms, "transfer_floor_note": "the step's inference H2D + D2H copies alone, both directions concurrently, all ranks at once"},
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "loss": nrc.GetLoss()}
+        if exchange_info is not None:
+            out["gradient_exchange"] = exchange_info
         if frame_tiles is not None:
             out["frame_4k_tiles"] = frame_tiles
         if world == 1:
@@ -449,7 +527,6 @@ def main():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--overlap", type=int, default=None, help="1: two-stream schedule (inference chunks under the optimizer / all-reduce); default: only for N > 1")
     ap.add_argument("--no-frame", action="store_true", help="skip the full-frame leg (tracking + NRC + compositing)")
     args = ap.parse_args()
     return run_reference(args) if args.impl == "reference" else run_ours(args)

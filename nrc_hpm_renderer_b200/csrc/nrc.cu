@@ -260,6 +260,7 @@ NrcCache::NrcCache(const NrcConfig& cfg, uint64_t seed) : cfg_(cfg) {
 NrcCache::~NrcCache() {
     for (auto e : pipe_events_) cudaEventDestroy(e);
     if (loss_pinned_) cudaFreeHost(loss_pinned_);
+    if (ov_inf_stream_) { cudaStreamDestroy(ov_inf_stream_); cudaStreamDestroy(ov_tr_stream_); for (auto e : ov_ev_) cudaEventDestroy(e); }
     if (ema_stream_) {
         cudaStreamSynchronize(ema_stream_);
         cudaStreamDestroy(ema_stream_);
@@ -352,6 +353,8 @@ void NrcCache::setup_kernels() {
         NRCHPM_CUDA(cudaFuncSetAttribute(nrc_forward2_kernel<IN_W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd2_smem_bytes<IN_W>(H, 1)));
         NRCHPM_CUDA(cudaFuncSetAttribute(nrc_backward2_kernel<IN_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd2_smem_bytes<IN_W>(H)));
         NRCHPM_CUDA(cudaFuncSetAttribute(nrc_infer_ws_kernel<IN_W, NRC_WS_NP, NRC_WS_NC, ws_slots(IN_W)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)infer_ws_smem_bytes<IN_W>(H, ws_slots(IN_W))));
+        if (const char* v = std::getenv("NRCHPM_WS_CARVEOUT"))      // experiment: shared-memory carve-out (percent) of the SMs that run the inference kernel
+            NRCHPM_CUDA(cudaFuncSetAttribute(nrc_infer_ws_kernel<IN_W, NRC_WS_NP, NRC_WS_NC, ws_slots(IN_W)>, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(v)));
         if (fused_training_fits()) {
             NRCHPM_CUDA(cudaFuncSetAttribute(nrc_train_fused_kernel<IN_W, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train_smem_bytes<IN_W>(H)));
             NRCHPM_CUDA(cudaFuncSetAttribute(nrc_train_fused_kernel<IN_W, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train_smem_bytes<IN_W>(H)));
@@ -361,6 +364,10 @@ void NrcCache::setup_kernels() {
     if (const char* v = std::getenv("NRCHPM_INFER_GROUPS")) infer_groups_ = std::max(0, std::min(3, std::atoi(v)));
     if (const char* v = std::getenv("NRCHPM_TRAIN_GROUPS")) train_groups_ = std::max(0, std::min(1, std::atoi(v)));
     if (const char* v = std::getenv("NRCHPM_INFER_WS")) infer_ws_ = std::atoi(v) != 0 ? 1 : 0;   // 0: tile-per-warpgroup kernel
+    if (const char* v = std::getenv("NRCHPM_OVERLAP")) overlap_schedule_ = std::atoi(v) != 0;          // data-parallel replicas: 0 = serial Inference() -> Train()
+    if (const char* v = std::getenv("NRCHPM_OVERLAP_HEAD")) overlap_head_ = std::max(0.0, std::min(1.0, std::atof(v)));
+    if (const char* v = std::getenv("NRCHPM_PEER_FUSED")) peer_fused_ = std::atoi(v) != 0;             // 0: gather / Adam / publish as three kernels
+    if (const char* v = std::getenv("NRCHPM_PEER_CTAS")) peer_ctas_ = (uint32_t)std::max(1, std::atoi(v));
     if (const char* v = std::getenv("NRCHPM_TRAIN_FUSED")) train_fused_ = std::atoi(v) != 0;          // 0: the three-kernel path
     if (const char* v = std::getenv("NRCHPM_TRAIN_TPR")) train_tpr_ = std::atoi(v) == 4 ? 4 : 2;      // threads per record of the fused kernel
     if (const char* v = std::getenv("NRCHPM_TRAIN_PROF")) if (std::atoi(v)) { train_prof_.allocate((size_t)sm_count_ * 16); train_prof_.zero(); timeline_.allocate(2 * kTimelineSlots); reset_timeline(); }   // development aid
@@ -395,9 +402,7 @@ void NrcCache::snapshot_params(bool use_ema, cudaStream_t s) {
 void NrcCache::inference_set(int param_set, const float* d_in, float* d_out, uint32_t n, const uint32_t* d_indices, const uint32_t* d_count, cudaStream_t s) {
     if (param_set != 2) { inference(d_in, d_out, n, param_set != 0, d_indices, d_count, s); return; }
     NRCHPM_REQUIRE(snapshot_valid_, "inference from the snapshot without nrc_snapshot_params");
-    infer_params_override_ = infer_snapshot_.ptr;
-    try { inference(d_in, d_out, n, true, d_indices, d_count, s); } catch (...) { infer_params_override_ = nullptr; throw; }
-    infer_params_override_ = nullptr;
+    inference_with(infer_snapshot_.ptr, d_in, d_out, n, d_indices, d_count, s, 0);
 }
 
 void NrcCache::encode(const float* d_in, uint32_t n, bool use_ema, void* d_out_half, cudaStream_t s) {
@@ -409,10 +414,18 @@ void NrcCache::encode(const float* d_in, uint32_t n, bool use_ema, void* d_out_h
 
 void NrcCache::inference(const float* d_in, float* d_out, uint32_t n, bool use_ema, const uint32_t* d_indices, const uint32_t* d_count, cudaStream_t s) {
     if (n == 0) return;
-    if (use_ema && !infer_params_override_) wait_ema(s);
+    if (use_ema) wait_ema(s);
+    inference_with(use_ema ? ema16_.ptr : w16_.ptr, d_in, d_out, n, d_indices, d_count, s, infer_max_ctas_);
+}
+
+// the inference launch on an explicit fp16 parameter vector [network | encoding]; max_ctas caps the persistent grid (0: whole GPU)
+void NrcCache::inference_with(const __half* params, const float* d_in, float* d_out, uint32_t n, const uint32_t* d_indices, const uint32_t* d_count, cudaStream_t s,
+                              uint32_t max_ctas) {
+    if (n == 0) return;
     FwdArgs a{};
-    a.enc = enc_; a.params = infer_params_override_ ? infer_params_override_ : use_ema ? ema16_.ptr : w16_.ptr; a.n_mlp = (uint32_t)n_mlp_; a.n_hidden = cfg_.n_hidden_layers;
+    a.enc = enc_; a.params = params; a.n_mlp = (uint32_t)n_mlp_; a.n_hidden = cfg_.n_hidden_layers;
     a.in = d_in; a.indices = d_indices; a.d_count = d_count; a.n = n; a.out = d_out;
+    a.tl = timeline_slot();
     const uint32_t tiles = (n + kTile - 1) / kTile;
     uint32_t grid, threads;
     if (infer_groups_ > 0) {
@@ -424,10 +437,12 @@ void NrcCache::inference(const float* d_in, float* d_out, uint32_t n, bool use_e
         check_launch("nrc_forward2_kernel<infer>");
         return;
     }
-    if (infer_ws_ > 0 && enc_.pos_enc == POS_HASHGRID && infer_max_ctas_ == 0 && tiles >= (uint32_t)sm_count_) {
+    if (infer_ws_ > 0 && enc_.pos_enc == POS_HASHGRID && tiles >= (uint32_t)sm_count_) {
         // warp-specialised persistent kernel: one CTA per SM, producer warpgroups encode, consumer warpgroups run the MLP
         grid = (uint32_t)sm_count_;
-        NRC_DISPATCH_INW(enc_.in_w, { nrc_infer_ws_kernel<IN_W, NRC_WS_NP, NRC_WS_NC, ws_slots(IN_W)><<<grid, (NRC_WS_NP + NRC_WS_NC) * 128, infer_ws_smem_bytes<IN_W>(cfg_.n_hidden_layers, ws_slots(IN_W)), s>>>(a); });
+        if (max_ctas) grid = std::min(grid, max_ctas);
+        // (same access-policy window as the training launches: kernels with different windows do not share the GPU)
+        NRC_DISPATCH_INW(enc_.in_w, { launch_hot(nrc_infer_ws_kernel<IN_W, NRC_WS_NP, NRC_WS_NC, ws_slots(IN_W)>, grid, (NRC_WS_NP + NRC_WS_NC) * 128, infer_ws_smem_bytes<IN_W>(cfg_.n_hidden_layers, ws_slots(IN_W)), s, a); });
         check_launch("nrc_infer_ws_kernel");
         return;
     }
@@ -435,11 +450,11 @@ void NrcCache::inference(const float* d_in, float* d_out, uint32_t n, bool use_e
     const uint32_t wgs = (uint32_t)std::max(1, std::min<int>(kInferWgs, (int)((tiles + sm_count_ * kInferCtas - 1) / (sm_count_ * kInferCtas))));
     threads = wgs * 128;
     grid = std::min<uint32_t>((tiles + wgs - 1) / wgs, (uint32_t)sm_count_ * kInferCtas);
-    if (infer_max_ctas_) grid = std::min(grid, infer_max_ctas_);          // leave room for a co-running kernel (NCCL all-reduce)
+    if (max_ctas) grid = std::min(grid, max_ctas);          // leave room for a co-running kernel (NCCL all-reduce)
     const size_t lvl_bytes = infer_smem_level_bytes();
     if (lvl_bytes) { a.smem_levels = NRC_SMEM_LEVELS; a.smem_level_entries = (uint32_t)(lvl_bytes / 4); }
     NRC_DISPATCH_INW(enc_.in_w, {
-        nrc_forward_kernel<IN_W, false><<<grid, threads, fwd_smem_bytes<IN_W>(cfg_.n_hidden_layers, (int)wgs) + lvl_bytes, s>>>(a);
+        launch_hot(nrc_forward_kernel<IN_W, false>, grid, threads, fwd_smem_bytes<IN_W>(cfg_.n_hidden_layers, (int)wgs) + lvl_bytes, s, a);
     });
     check_launch("nrc_forward_kernel<infer>");
 }
@@ -580,13 +595,46 @@ void NrcCache::optimizer_step(cudaStream_t s) {
     // ---- one launch: network weights (first n_mlp / 64 CTAs) + Adam on the touched hash-grid entries
     if (ema_in_flight_) NRCHPM_CUDA(cudaStreamWaitEvent(s, ema_done_, 0));        // the previous step's EMA pass still reads the weights
     a.mlp_blocks = (uint32_t)(n_mlp_ / 64);
-    const unsigned grid_blocks = has_grid ? (unsigned)(((n_params_ - n_mlp_) / 8 + 255) / 256) : 0u;
-    launch_hot(nrc_adam_kernel, a.mlp_blocks + grid_blocks, 256, 0, s, a);
-    check_launch("nrc_adam_kernel");
+    a.grid_begin = n_mlp_; a.grid_end = n_params_;
+    const bool sharded = peer_sharded_step_ && has_grid;
+    if (sharded) {                  // data-parallel replica: this rank updates its own slice of the encoding only (peer_exchange left the summed gradient there)
+        uint64_t b, e;
+        peer_slice(b, e);
+        a.grid_begin = n_mlp_ + b * 8; a.grid_end = n_mlp_ + e * 8;
+    }
+    peer_sharded_step_ = false;
+    const unsigned grid_blocks = has_grid ? (unsigned)(((a.grid_end - a.grid_begin) / 8 + 255) / 256) : 0u;
+    if (sharded && peer_fused_) {
+        // reduce-scatter + Adam on the slice + weight all-gather in ONE kernel over peer memory, then wait for every peer's final flag
+        PeerArgs pa{};
+        fill_peer_args(pa);
+        cudaLaunchConfig_t cfg = {};
+        const unsigned spans_per_cta = peer_world_ <= 2 ? 2u : 1u;       // nrc_peer_adam_kernel: U spans per warp
+        cfg.gridDim = a.mlp_blocks + (grid_blocks + spans_per_cta - 1) / spans_per_cta; cfg.blockDim = 256; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        if (l2_window_bytes_) {
+            attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+            attr[0].val.accessPolicyWindow.base_ptr = hot_.ptr; attr[0].val.accessPolicyWindow.num_bytes = l2_window_bytes_;
+            attr[0].val.accessPolicyWindow.hitRatio = l2_hit_ratio_; attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+        }
+        if (peer_world_ <= 2) NRCHPM_CUDA(cudaLaunchKernelEx(&cfg, nrc_peer_adam_kernel<2>, a, pa));
+        else if (peer_world_ <= 4) NRCHPM_CUDA(cudaLaunchKernelEx(&cfg, nrc_peer_adam_kernel<4>, a, pa));
+        else NRCHPM_CUDA(cudaLaunchKernelEx(&cfg, nrc_peer_adam_kernel<8>, a, pa));
+        check_launch("nrc_peer_adam_kernel");
+        nrc_peer_wait_kernel<<<1, 32, 0, s>>>(peer_flag_words_.ptr, peer_world_, pa.token);
+        check_launch("nrc_peer_wait_kernel");
+    } else {
+        launch_hot(nrc_adam_kernel, a.mlp_blocks + grid_blocks, 256, 0, s, a);
+        check_launch("nrc_adam_kernel");
+        if (sharded) peer_publish(s);   // ... and receives everybody else's
+    }
     if (has_grid) {
         // ---- the dense EMA of the hash-grid weights, which only Inference() reads: side stream, underneath the next step
         NRCHPM_CUDA(cudaEventRecord(adam_done_, s));
         NRCHPM_CUDA(cudaStreamWaitEvent(ema_stream_, adam_done_, 0));
+        if (ema_gate_) { NRCHPM_CUDA(cudaStreamWaitEvent(ema_stream_, ema_gate_, 0)); ema_gate_ = nullptr; }   // a snapshot copy still reads the EMA weights
         launch_hot(nrc_grid_ema_kernel, (unsigned)sm_count_, 256, 0, ema_stream_, a);
         check_launch("nrc_grid_ema_kernel");
         NRCHPM_CUDA(cudaEventRecord(ema_done_, ema_stream_));
@@ -719,9 +767,79 @@ void NrcCache::signal_finished() {
 void NrcCache::infer_and_train(const uint32_t* filter_host, bool train) {
     NRCHPM_REQUIRE(initialised_, "nrc_init has not been called");
     wait_start();
-    run_inference(filter_host);
-    if (train) run_train();
+    bool all_batches = true;
+    if (filter_host) for (size_t i = 0; i < infer_batches_.size(); i++) all_batches &= filter_host[i] != 0;
+    if (train && peer_world_ >= 2 && overlap_schedule_ && all_batches && infer_count_ > 0) {
+        infer_and_train_overlapped();
+    } else {
+        run_inference(filter_host);
+        if (train) run_train();
+    }
     signal_finished();
+}
+
+// Optional schedule (NRCHPM_OVERLAP=1) of InferAndTrain on a data-parallel replica (nrc_peer_setup).  It pays with the
+// step-by-step exchange (NRCHPM_PEER_FUSED=0: ~50 us reduce-scatter + ~30 us all-gather windows per training step at two ranks); with
+// the default fused peer kernel (nrc_peer_adam_kernel, ~40 us per step, SMs busy) the serial Inference() -> Train() order is faster
+// (measured, profiles/r02_summary.md).  Every training step waits for the gradient exchange over
+// NVLink, during which the SMs would idle; the frame's inference -- which in the reference's order runs first, on the weights of the
+// previous frame -- is therefore cut into one chunk per training step and each chunk runs underneath that step's exchange + optimizer
+// (stream s_inf) from a snapshot of the pre-training EMA weights, which keeps the reference's result.  The forward / backward kernel of
+// the next step gets the whole GPU again: it waits for the chunk (it could not share an SM with the inference CTAs anyway: shared
+// memory).  `overlap_head_` of the records can be evaluated up front at full occupancy when the windows are too short.
+void NrcCache::infer_and_train_overlapped() {
+    if (!ov_inf_stream_) {
+        int prio_lo = 0, prio_hi = 0;
+        NRCHPM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        NRCHPM_CUDA(cudaStreamCreateWithPriority(&ov_inf_stream_, cudaStreamNonBlocking, prio_lo));
+        NRCHPM_CUDA(cudaStreamCreateWithPriority(&ov_tr_stream_, cudaStreamNonBlocking, prio_hi));
+        for (auto& e : ov_ev_) NRCHPM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const uint32_t B = cfg_.train_batch_size, nb = cfg_.train_batch_count, n = infer_count_;
+    NRCHPM_REQUIRE(nb <= kMaxOverlapBatches, "overlapped schedule: too many training batches per frame");
+    cudaStream_t si = ov_inf_stream_, st = ov_tr_stream_;
+    cudaEvent_t ev_begin = ov_ev_[0], ev_snap = ov_ev_[1], ev_inf_done = ov_ev_[2], ev_tr_done = ov_ev_[3];
+    NRCHPM_CUDA(cudaEventRecord(ev_begin, stream_));
+    NRCHPM_CUDA(cudaStreamWaitEvent(si, ev_begin, 0));
+    NRCHPM_CUDA(cudaStreamWaitEvent(st, ev_begin, 0));
+    // snapshot of the EMA weights Inference() has to see; only the first EMA pass of this frame's training overwrites them
+    infer_snapshot_.ensure(n_params_);
+    wait_ema(si);
+    NRCHPM_CUDA(cudaMemcpyAsync(infer_snapshot_.ptr, ema16_.ptr, n_params_ * sizeof(__half), cudaMemcpyDeviceToDevice, si));
+    NRCHPM_CUDA(cudaEventRecord(ev_snap, si));
+    ema_gate_ = ev_snap;                                                // consumed by the next optimizer_step
+    uint32_t off = 0;
+    const uint32_t head = std::min(n, (uint32_t)((double)n * overlap_head_) / kTile * kTile);
+    if (head) {
+        inference_with(infer_snapshot_.ptr, infer_in_, infer_out_, head, nullptr, nullptr, si, 0);
+        NRCHPM_CUDA(cudaEventRecord(ov_ev_[4], si));
+        NRCHPM_CUDA(cudaStreamWaitEvent(st, ov_ev_[4], 0));
+        off = head;
+    }
+    uint32_t chunk = (n - off + nb - 1) / nb;
+    chunk = (chunk + kTile - 1) / kTile * kTile;
+    peer_one_cta_per_sm_ = true;                                        // fits next to an inference CTA on every SM
+    for (uint32_t b = 0; b < nb; b++) {
+        cudaEvent_t ev_bwd = ov_ev_[5 + 2 * b], ev_chunk = ov_ev_[6 + 2 * b];
+        training_step(train_in_ + 5 * (size_t)b * B, train_target_ + 3 * (size_t)b * B, B, false, st);
+        NRCHPM_CUDA(cudaEventRecord(ev_bwd, st));
+        peer_exchange(st);
+        NRCHPM_CUDA(cudaStreamWaitEvent(si, ev_bwd, 0));
+        const uint32_t m = b + 1 < nb ? std::min(chunk, n - off) : n - off;
+        if (m) inference_with(infer_snapshot_.ptr, infer_in_ + 5 * (size_t)off, infer_out_ + 3 * (size_t)off, m, nullptr, nullptr, si, 0);
+        off += m;
+        NRCHPM_CUDA(cudaEventRecord(ev_chunk, si));
+        // the exchange kernels (one 48-register CTA per SM) and the optimizer on this rank's slice (small CTAs) share the SMs with the
+        // chunk; the next forward / backward kernel (192 KB of shared memory per CTA) gets the whole GPU: it waits for the chunk
+        optimizer_step(st);
+        NRCHPM_CUDA(cudaStreamWaitEvent(st, ev_chunk, 0));
+    }
+    peer_one_cta_per_sm_ = false;
+    NRCHPM_CUDA(cudaEventRecord(ev_inf_done, si));
+    NRCHPM_CUDA(cudaEventRecord(ev_tr_done, st));
+    NRCHPM_CUDA(cudaStreamWaitEvent(stream_, ev_inf_done, 0));
+    NRCHPM_CUDA(cudaStreamWaitEvent(stream_, ev_tr_done, 0));
+    train_stream_last_ = stream_;                                       // loss(): everything above is ordered before stream_ now
 }
 
 }  // namespace nrchpm
@@ -838,7 +956,7 @@ void NrcCache::gradient_buffers(float** mlp, void** enc) {
 void NrcCache::peer_export(uint8_t* out) {
     NRCHPM_REQUIRE(n_grid_ % 8 == 0, "peer exchange needs the encoding gradient to be a multiple of 16 bytes");
     mlp_grad_f32_.ensure(n_mlp_); mlp_sum_.ensure(n_mlp_);
-    if (!peer_flag_words_.ptr) { peer_flag_words_.allocate(2 * kMaxPeers); peer_flag_words_.zero(); peer_done_.allocate(1); peer_done_.zero(); }
+    if (!peer_flag_words_.ptr) { peer_flag_words_.allocate(3 * kMaxPeers); peer_flag_words_.zero(); peer_done_.allocate(1); peer_done_.zero(); }
     NRCHPM_CUDA(cudaDeviceSynchronize());
     cudaIpcMemHandle_t h[3];
     NRCHPM_CUDA(cudaIpcGetMemHandle(&h[0], grad16_.ptr));
@@ -860,27 +978,62 @@ void NrcCache::peer_setup(int rank, int world, const uint8_t* handles) {
     }
     peer_rank_ = rank; peer_world_ = world;
 }
-void NrcCache::peer_exchange(cudaStream_t s) {
-    NRCHPM_REQUIRE(peer_world_ >= 2, "nrc_peer_exchange before nrc_peer_setup");
-    NRCHPM_REQUIRE(grads_pending_ && !dw_source_, "nrc_peer_exchange: call nrc_training_step(run_optimizer=0) first");
-    nrc_reduce_partials_kernel<<<(unsigned)((n_mlp_ + 63) / 64), 256, 0, s>>>(dw_partials_.ptr, dw_chunks_, (uint32_t)n_mlp_, mlp_grad_f32_.ptr);
-    check_launch("nrc_reduce_partials_kernel");
-    PeerArgs a{};
-    a.rank = peer_rank_; a.world = peer_world_; a.token = ++peer_token_;
+// own slice of the hash-grid entries, in int4 words (warp-aligned: 32 words = the 256 parameters one optimizer warp owns)
+void NrcCache::peer_slice(uint64_t& begin, uint64_t& end) const {
+    const uint64_t n_vec = n_grid_ / 8;
+    uint64_t per = (n_vec + peer_world_ - 1) / peer_world_;
+    per = (per + 31) / 32 * 32;
+    begin = std::min(n_vec, per * (uint64_t)peer_rank_);
+    end = std::min(n_vec, begin + per);
+}
+void NrcCache::fill_peer_args(PeerArgs& a) {
+    a.rank = peer_rank_; a.world = peer_world_; a.token = peer_token_;
+    const size_t n_pad = (n_params_ + 63) / 64 * 64;
     for (int p = 0; p < peer_world_; p++) {
-        a.grad[p] = reinterpret_cast<int4*>(reinterpret_cast<__half*>(peer_grad_[p]) + n_mlp_);
+        __half* base = reinterpret_cast<__half*>(peer_grad_[p]);                 // [grad16 | w16] of rank p
+        a.grad[p] = reinterpret_cast<int4*>(base + n_mlp_);
+        a.w16[p] = reinterpret_cast<int4*>(base + n_pad + n_mlp_);
         a.mlp[p] = reinterpret_cast<const float*>(peer_mlp_[p]);
         a.flags[p] = reinterpret_cast<uint32_t*>(peer_flags_[p]);
     }
     a.mlp_sum = mlp_sum_.ptr; a.n_vec = n_grid_ / 8; a.n_mlp = (uint32_t)n_mlp_; a.done_counter = peer_done_.ptr;
-    if (peer_world_ <= 2) nrc_peer_reduce_kernel<2><<<sm_count_ * 2, 256, 0, s>>>(a);
-    else if (peer_world_ <= 4) nrc_peer_reduce_kernel<4><<<sm_count_ * 2, 256, 0, s>>>(a);
-    else nrc_peer_reduce_kernel<8><<<sm_count_ * 2, 256, 0, s>>>(a);
-    check_launch("nrc_peer_reduce_kernel");
-    nrc_peer_wait_kernel<<<1, 32, 0, s>>>(peer_flag_words_.ptr, peer_world_, a.token);
-    check_launch("nrc_peer_wait_kernel");
+    peer_slice(a.slice_begin, a.slice_end);
+}
+// step 1 of the sharded optimizer step (nrc_peer_gather_kernel): afterwards this rank's gradient buffer holds the SUM over the ranks on
+// its own slice and zeros elsewhere; nrc_optimizer_step then updates the slice and publishes the new weights to every peer
+void NrcCache::peer_exchange(cudaStream_t s) {
+    NRCHPM_REQUIRE(peer_world_ >= 2, "nrc_peer_exchange before nrc_peer_setup");
+    NRCHPM_REQUIRE(grads_pending_ && !dw_source_, "nrc_peer_exchange: call nrc_training_step(run_optimizer=0) first");
+    NRCHPM_REQUIRE(n_mlp_ % 8 == 0 && ((n_params_ + 63) / 64 * 64 + n_mlp_) % 8 == 0, "peer exchange: the encoding part of the fp16 vectors must be 16-byte aligned");
+    // round A also tells the peers that this rank's previous EMA pass is done with the weights they are about to overwrite
+    if (ema_in_flight_) NRCHPM_CUDA(cudaStreamWaitEvent(s, ema_done_, 0));
+    nrc_reduce_partials_kernel<<<(unsigned)((n_mlp_ + 63) / 64), 256, 0, s>>>(dw_partials_.ptr, dw_chunks_, (uint32_t)n_mlp_, mlp_grad_f32_.ptr);
+    check_launch("nrc_reduce_partials_kernel");
+    ++peer_token_;
+    if (!peer_fused_) {             // step-by-step form: reduce-scatter now, Adam on the slice and the weight all-gather in nrc_optimizer_step
+        PeerArgs a{};
+        fill_peer_args(a);
+        a.tl = timeline_slot();
+        const unsigned ctas = peer_ctas_ ? peer_ctas_ : (unsigned)sm_count_ * (peer_one_cta_per_sm_ ? 1 : 2);
+        if (peer_world_ <= 2) launch_hot(nrc_peer_gather_kernel<2>, ctas, 256, 0, s, a);
+        else if (peer_world_ <= 4) launch_hot(nrc_peer_gather_kernel<4>, ctas, 256, 0, s, a);
+        else launch_hot(nrc_peer_gather_kernel<8>, ctas, 256, 0, s, a);
+        check_launch("nrc_peer_gather_kernel");
+    }
     dw_source_ = mlp_sum_.ptr;
     grad_scale_ = (float)peer_world_;
+    peer_sharded_step_ = true;
+}
+// step 3: all-gather of the weight slices, then wait until every peer's slice has landed here
+void NrcCache::peer_publish(cudaStream_t s) {
+    PeerArgs a{};
+    fill_peer_args(a);
+    a.tl = timeline_slot();
+    const unsigned ctas = peer_ctas_ ? peer_ctas_ : (unsigned)sm_count_ * (peer_one_cta_per_sm_ ? 1 : 2);
+    launch_hot(nrc_peer_publish_kernel, ctas, 256, 0, s, a);
+    check_launch("nrc_peer_publish_kernel");
+    nrc_peer_wait_kernel<<<1, 32, 0, s>>>(peer_flag_words_.ptr, peer_world_, a.token);
+    check_launch("nrc_peer_wait_kernel");
 }
 
 // Host-buffer inference: the records are cut into chunks of whole persistent-grid rounds and pipelined over three streams
@@ -902,13 +1055,13 @@ void NrcCache::ensure_pipeline(uint32_t n_chunks) {
     }
 }
 // queues the chunked H2D -> kernel -> D2H pipeline; returns without waiting
-void NrcCache::queue_inference_pipeline(const float* h_in, float* h_out, uint32_t n, bool use_ema, uint32_t chunk, uint32_t n_chunks) {
+void NrcCache::queue_inference_pipeline(const __half* params, const float* h_in, float* h_out, uint32_t n, uint32_t chunk, uint32_t n_chunks) {
     for (uint32_t c = 0; c < n_chunks; c++) {
         const uint32_t o = c * chunk, m = std::min(chunk, n - o);
         NRCHPM_CUDA(cudaMemcpyAsync(host_in_.ptr + (size_t)o * 5, h_in + (size_t)o * 5, (size_t)m * 5 * sizeof(float), cudaMemcpyHostToDevice, copy_in_stream_));
         NRCHPM_CUDA(cudaEventRecord(pipe_events_[2 * c], copy_in_stream_));
         NRCHPM_CUDA(cudaStreamWaitEvent(compute_stream_, pipe_events_[2 * c], 0));
-        inference(host_in_.ptr + (size_t)o * 5, host_out_.ptr + (size_t)o * 3, m, use_ema, nullptr, nullptr, compute_stream_);
+        inference_with(params, host_in_.ptr + (size_t)o * 5, host_out_.ptr + (size_t)o * 3, m, nullptr, nullptr, compute_stream_, 0);
         NRCHPM_CUDA(cudaEventRecord(pipe_events_[2 * c + 1], compute_stream_));
         NRCHPM_CUDA(cudaStreamWaitEvent(copy_out_stream_, pipe_events_[2 * c + 1], 0));
         NRCHPM_CUDA(cudaMemcpyAsync(h_out + (size_t)o * 3, host_out_.ptr + (size_t)o * 3, (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToHost, copy_out_stream_));
@@ -925,7 +1078,8 @@ void NrcCache::inference_host(const float* h_in, float* h_out, uint32_t n, bool 
     NRCHPM_CUDA(cudaEventRecord(ev_prev, stream_));
     NRCHPM_CUDA(cudaStreamWaitEvent(compute_stream_, ev_prev, 0));
     NRCHPM_CUDA(cudaStreamWaitEvent(copy_in_stream_, ev_prev, 0));
-    queue_inference_pipeline(h_in, h_out, n, use_ema, chunk, n_chunks);
+    if (use_ema) wait_ema(compute_stream_);
+    queue_inference_pipeline(use_ema ? ema16_.ptr : w16_.ptr, h_in, h_out, n, chunk, n_chunks);
     NRCHPM_CUDA(cudaStreamSynchronize(copy_out_stream_));
 }
 void NrcCache::training_step_host(const float* h_in, const float* h_tgt, uint32_t B, float* loss_out) {
@@ -965,7 +1119,6 @@ void NrcCache::infer_and_train_host(const float* h_in, float* h_out, uint32_t n,
         NRCHPM_CUDA(cudaMemcpyAsync(infer_snapshot_.ptr, use_ema ? ema16_.ptr : w16_.ptr, n_params_ * sizeof(__half), cudaMemcpyDeviceToDevice, compute_stream_));
         NRCHPM_CUDA(cudaEventRecord(ev_snap, compute_stream_));
         NRCHPM_CUDA(cudaStreamWaitEvent(train_stream_, ev_snap, 0));        // training overwrites what the snapshot copy reads
-        infer_params_override_ = infer_snapshot_.ptr;
     }
     if (train) {
         NRCHPM_CUDA(cudaMemcpyAsync(host_tin_.ptr, h_tin, T * 5 * sizeof(float), cudaMemcpyHostToDevice, copy_in_stream_));
@@ -978,8 +1131,15 @@ void NrcCache::infer_and_train_host(const float* h_in, float* h_out, uint32_t n,
     // The inference kernels wait for the last optimizer step; their H2D copies do not.  Inference still evaluates the snapshot.
     if (train) {
         NRCHPM_CUDA(cudaStreamWaitEvent(ts, ev_train, 0));
-        for (uint32_t b = 0; b < n_batches; b++)
-            training_step(host_tin_.ptr + (size_t)b * B * 5, host_tgt_.ptr + (size_t)b * B * 3, B, true, ts);
+        for (uint32_t b = 0; b < n_batches; b++) {
+            if (peer_world_ >= 2) {      // data-parallel replica: mean gradient over the ranks
+                training_step(host_tin_.ptr + (size_t)b * B * 5, host_tgt_.ptr + (size_t)b * B * 3, B, false, ts);
+                peer_exchange(ts);
+                optimizer_step(ts);
+            } else {
+                training_step(host_tin_.ptr + (size_t)b * B * 5, host_tgt_.ptr + (size_t)b * B * 3, B, true, ts);
+            }
+        }
         if (!loss_pinned_) NRCHPM_CUDA(cudaMallocHost((void**)&loss_pinned_, sizeof(float)));   // pageable memory would make this copy block the host
         NRCHPM_CUDA(cudaMemcpyAsync(loss_pinned_, loss_dev_.ptr, sizeof(float), cudaMemcpyDeviceToHost, ts));
         if (overlap) {
@@ -987,10 +1147,10 @@ void NrcCache::infer_and_train_host(const float* h_in, float* h_out, uint32_t n,
             NRCHPM_CUDA(cudaStreamWaitEvent(compute_stream_, ev_trained, 0));
         }
     }
-    try {
-        if (n) queue_inference_pipeline(h_in, h_out, n, use_ema, chunk, n_chunks);
-    } catch (...) { infer_params_override_ = nullptr; throw; }
-    infer_params_override_ = nullptr;
+    if (n) {
+        if (!overlap && use_ema) wait_ema(compute_stream_);
+        queue_inference_pipeline(overlap ? infer_snapshot_.ptr : (use_ema ? ema16_.ptr : w16_.ptr), h_in, h_out, n, chunk, n_chunks);
+    }
     // later work on the cache's own stream is ordered behind this call
     NRCHPM_CUDA(cudaEventRecord(ev_done, compute_stream_));
     NRCHPM_CUDA(cudaStreamWaitEvent(stream_, ev_done, 0));

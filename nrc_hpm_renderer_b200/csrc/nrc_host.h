@@ -69,6 +69,9 @@ public:
     void peer_export(uint8_t* out);
     void peer_setup(int rank, int world, const uint8_t* handles);
     void peer_exchange(cudaStream_t s);
+    void peer_publish(cudaStream_t s);
+    void peer_slice(uint64_t& begin, uint64_t& end) const;
+    void fill_peer_args(struct PeerArgs& a);
     void last_step_tensor(int which, float* host_out);
     uint32_t train_profile(long long* host_out, uint32_t max_ctas);
     uint32_t read_timeline(unsigned long long* host_out, uint32_t max_slots);
@@ -85,7 +88,9 @@ private:
     void training_step_three_kernels(const float* d_in, const float* d_target, uint32_t B, cudaStream_t s);
     void launch_shape(uint32_t tiles, uint32_t& grid, uint32_t& threads) const;
     void ensure_pipeline(uint32_t n_chunks);
-    void queue_inference_pipeline(const float* h_in, float* h_out, uint32_t n, bool use_ema, uint32_t chunk, uint32_t n_chunks);
+    void queue_inference_pipeline(const __half* params, const float* h_in, float* h_out, uint32_t n, uint32_t chunk, uint32_t n_chunks);
+    void inference_with(const __half* params, const float* d_in, float* d_out, uint32_t n, const uint32_t* d_indices, const uint32_t* d_count, cudaStream_t s, uint32_t max_ctas);
+    void infer_and_train_overlapped();
 
     NrcConfig cfg_;
     EncParams enc_;
@@ -134,10 +139,17 @@ private:
     cudaStream_t copy_in_stream_ = nullptr, copy_out_stream_ = nullptr, compute_stream_ = nullptr;   // host-buffer pipeline
     cudaStream_t train_stream_ = nullptr;            // InferAndTrain on host buffers: training overlaps the inference pipeline
     DeviceBuffer<__half> infer_snapshot_;            // ... which then reads a snapshot of the pre-training parameters
-    const __half* infer_params_override_ = nullptr;
     bool snapshot_valid_ = false;
+    // data-parallel replicas: InferAndTrain with the frame's inference underneath the gradient exchanges (infer_and_train_overlapped)
+    static constexpr uint32_t kMaxOverlapBatches = 16;
+    cudaStream_t ov_inf_stream_ = nullptr, ov_tr_stream_ = nullptr;
+    cudaEvent_t ov_ev_[5 + 2 * kMaxOverlapBatches] = {};
+    cudaEvent_t ema_gate_ = nullptr;
+    bool overlap_schedule_ = false, peer_one_cta_per_sm_ = false; double overlap_head_ = 0.0; uint32_t peer_ctas_ = 0;
     int peer_rank_ = -1, peer_world_ = 0;
     uint32_t peer_token_ = 0;
+    bool peer_fused_ = true;                         // reduce-scatter + Adam + weight all-gather as one kernel (nrc_peer_adam_kernel)
+    bool peer_sharded_step_ = false;                 // peer_exchange ran: the pending optimizer step covers this rank's slice and ends with the weight all-gather
     float grad_scale_ = 1.0f;                        // ranks whose gradients were summed into the buffers (the optimizer divides)
     void* peer_grad_[8] = {}; void* peer_mlp_[8] = {}; void* peer_flags_[8] = {};
     DeviceBuffer<float> mlp_sum_;

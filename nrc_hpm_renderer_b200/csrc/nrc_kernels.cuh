@@ -531,6 +531,7 @@ struct FwdArgs {
     __half* dout16;             // [n][16]     dL/doutput * loss_scale
     float* loss_partials;       // [n/128]
     float loss_scale;
+    unsigned long long* tl;     // optional device-side timeline slot (development aid)
 };
 
 constexpr uint32_t kColD = 0, kColA = 96, kColsPerWg = 128;
@@ -801,7 +802,9 @@ __host__ __device__ constexpr size_t infer_ws_smem_bytes(int n_hidden, int slots
 }
 
 template <int IN_W, int NP, int NC, int NS>
-__global__ void __launch_bounds__((NP + NC) * 128, 1) nrc_infer_ws_kernel(const __grid_constant__ FwdArgs a) {
+// 80 registers (640 threads -> 51 200 of the SM's 65 536): a 256-thread CTA of the gradient-exchange kernel (48 registers) fits next to it,
+// which is what lets a data-parallel replica run its inference underneath the exchanges (NrcCache::infer_and_train_overlapped)
+__global__ void __maxnreg__(80) nrc_infer_ws_kernel(const __grid_constant__ FwdArgs a) {
     using namespace tc05;
     constexpr uint32_t kAlloc = NC <= 1 ? 128u : NC == 2 ? 256u : 512u;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -814,6 +817,7 @@ __global__ void __launch_bounds__((NP + NC) * 128, 1) nrc_infer_ws_kernel(const 
     uint8_t* wo_s = wh_s + (H - 1) * 8192;
     uint8_t* ring = wo_s + 2048;
 
+    timeline_begin(a.tl, 0);
     if (warp == 0) { tmem_alloc(&tmem_base_s, kAlloc); tmem_relinquish(); }
     if (tid == 0) {
         for (int s = 0; s < NS; s++) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
@@ -937,6 +941,7 @@ __global__ void __launch_bounds__((NP + NC) * 128, 1) nrc_infer_ws_kernel(const 
     }
     fence_before();
     __syncthreads();
+    timeline_end(a.tl, 0);
     if (warp == 0) tmem_dealloc(tmem_base_s, kAlloc);
 }
 
@@ -1970,6 +1975,7 @@ struct OptArgs {
     const float* partials;
     uint32_t n_chunks;
     uint32_t mlp_blocks;        // nrc_adam_kernel: CTAs [0, mlp_blocks) own 64 network weights each
+    uint64_t grid_begin, grid_end;   // parameter range the hash-grid CTAs cover (the whole encoding; a data-parallel rank's own slice)
     float lr, beta1, beta2, eps, l2_reg, loss_scale, ema_decay, ema_debias_old, ema_debias_new, log2_beta1, log2_beta2;
     unsigned long long* tl;     // optional device-side timeline slots (development aid)
     unsigned long long* tl_ema;
@@ -2038,13 +2044,13 @@ __global__ void __launch_bounds__(256, NRC_OPT_MIN_BLOCKS) nrc_adam_kernel(const
         return;
     }
     const uint32_t gb = blockIdx.x - a.mlp_blocks;
-    const uint64_t i0 = a.n_mlp + ((uint64_t)gb * 256 + threadIdx.x) * 8;
-    const uint64_t warp_i0 = a.n_mlp + ((uint64_t)gb * 256 + warp * 32) * 8;
-    if (warp_i0 >= a.n_params) return;     // whole warp out of range
+    const uint64_t i0 = a.grid_begin + ((uint64_t)gb * 256 + threadIdx.x) * 8;
+    const uint64_t warp_i0 = a.grid_begin + ((uint64_t)gb * 256 + warp * 32) * 8;
+    if (warp_i0 >= a.grid_end) return;     // whole warp out of range
     union V8 { int4 v; uint32_t u[4]; };
     V8 g;
     g.v = make_int4(0, 0, 0, 0);
-    if (i0 < a.n_params) g.v = *reinterpret_cast<const int4*>(a.grad16 + i0);
+    if (i0 < a.grid_end) g.v = *reinterpret_cast<const int4*>(a.grad16 + i0);
     uint32_t base = 0, my_rank[4];
     bool mine[4];
 #pragma unroll
@@ -2133,32 +2139,43 @@ __global__ void __launch_bounds__(256) nrc_grid_state_gather_kernel(const GridAd
     else { dst[2 * i] = f[0]; dst[2 * i + 1] = f[1]; }
 }
 
-// ---------------------------------------------------------------------------------------------- data-parallel gradient exchange
-// One kernel per training step replaces the NCCL all-reduce of the gradients: every rank owns 1/world of the
-// hash-grid entries, reads that slice of every peer's fp16 gradient straight out of the peer's HBM over NVLink (P2P loads, buffers
-// shared with cudaIpc), sums in rank order (fp32) and stores the sum into every rank's gradient buffer (P2P stores) -- reduce-
-// scatter and all-gather in one pass, 2 * (world-1)/world * 28.5 MB on the wire per rank, and nothing at all for entries no rank
-// touched (the common case on the fine levels).  The small fp32 MLP gradient is summed redundantly by every rank, in rank order,
-// so all replicas hold bit-identical results.  Synchronisation: two flag rounds in peer-visible memory (system-scope release /
-// acquire): "my gradients are complete" before the first peer load, "my stores have landed" before the optimizer may run.
+// ---------------------------------------------------------------------------------------------- data-parallel training over peer memory
+// Replaces the NCCL all-reduce a data-parallel tcnn would need with a SHARDED optimizer step over NVLink peer memory
+// (buffers shared with cudaIpc).  Every rank owns 1/world of the hash-grid entries:
+//   1. nrc_peer_gather_kernel   reduce-scatter: the rank reads ITS slice of every peer's fp16 gradient straight out of the peer's HBM
+//                               (P2P loads), sums in rank order in fp32, keeps the sum in its own gradient buffer and writes zeros back
+//                               over the peers' words it consumed (so nobody needs a 28.5 MB memset).  The small fp32 MLP gradient is
+//                               summed redundantly by every rank, in rank order.
+//   2. nrc_adam_kernel          Adam on the rank's own slice only (plus the network weights, redundantly and identically everywhere):
+//                               at eight ranks the union of the touched entries is ~90 % of the tables, a replicated optimizer would
+//                               stream 4x the single-GPU state per step; sharded, every rank updates 1/8 of it.
+//   3. nrc_peer_publish_kernel  all-gather: the rank stores its updated fp16 weight slice into every peer's weight vector (P2P stores).
+// Replicas therefore hold bit-identical fp16 weights (working and EMA) after every step; the fp32 master weights and Adam moments of
+// a slice live on its owner only.  Synchronisation: three flag rounds in peer-visible memory (system-scope release / acquire):
+// A "my backward pass is complete, my previous EMA pass has read the weights", B "I am done reading and clearing your gradients",
+// C "my weight slice has landed in your buffer".
 constexpr int kMaxPeers = 8;
 struct PeerArgs {
     int rank, world;
     int4* grad[kMaxPeers];             // hash-grid gradient of every rank (own buffer at [rank]), 8 halfs per int4
+    int4* w16[kMaxPeers];              // hash-grid fp16 weights of every rank
     const float* mlp[kMaxPeers];       // fp32 MLP gradient of every rank
-    uint32_t* flags[kMaxPeers];        // flags[q]: rank q's flag words [2][kMaxPeers]; slot [phase][p] is written by rank p
+    uint32_t* flags[kMaxPeers];        // flags[q]: rank q's flag words [3][kMaxPeers]; slot [round][p] is written by rank p
     float* mlp_sum;                    // local: sum over the ranks
     uint64_t n_vec;                    // int4 words of the hash-grid gradient
+    uint64_t slice_begin, slice_end;   // this rank's slice, in int4 words
     uint32_t n_mlp;
     uint32_t token;                    // exchange counter, identical on every rank
     unsigned int* done_counter;        // local
+    unsigned long long* tl;            // optional device-side timeline slot (development aid)
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
 template <int WORLD>      // upper bound of a.world: 2, 4 or 8 (sizes the register tile of in-flight peer loads)
-__global__ void __launch_bounds__(256) nrc_peer_reduce_kernel(const __grid_constant__ PeerArgs a) {
+__global__ void __maxnreg__(48) nrc_peer_gather_kernel(const __grid_constant__ PeerArgs a) {
+    timeline_begin(a.tl, 0);
     // ---- round A: every rank's backward pass has finished (stream order makes that true for this rank at kernel start)
     if (blockIdx.x == 0 && threadIdx.x < a.world) st_release_sys(a.flags[threadIdx.x] + a.rank, a.token);
     if (threadIdx.x < a.world) while ((int32_t)(ld_acquire_sys(a.flags[a.rank] + threadIdx.x) - a.token) < 0) { }
@@ -2169,18 +2186,18 @@ __global__ void __launch_bounds__(256) nrc_peer_reduce_kernel(const __grid_const
         for (int p = 0; p < a.world; p++) sum += a.mlp[p][i];
         a.mlp_sum[i] = sum;
     }
-    const uint64_t per = (a.n_vec + a.world - 1) / a.world, begin = per * a.rank, end = min(begin + per, a.n_vec);
-    // four independent 16-byte words per thread and round: all peer loads of a round are in flight together (a remote load costs
-    // ~1 us of NVLink latency; 75 776 threads x 4 x 16 B = 4.8 MB in flight per peer keeps the links busy; 8 / WORLD words per peer so that the tile stays at 32 registers)
+    // 8 / WORLD independent 16-byte words per peer, thread and round: all peer loads of a round are in flight together (a remote load
+    // costs ~1 us of NVLink latency); the register tile stays at 32 registers
     constexpr int kU = 8 / WORLD;
-    for (uint64_t i0 = begin + gtid; i0 < end; i0 += stride * kU) {
+    const int4 zero = make_int4(0, 0, 0, 0);
+    for (uint64_t i0 = a.slice_begin + gtid; i0 < a.slice_end; i0 += stride * kU) {
         int4 v[WORLD][kU];
 #pragma unroll
         for (int u = 0; u < kU; u++) {
             const uint64_t i = i0 + (uint64_t)u * stride;
 #pragma unroll
             for (int p = 0; p < WORLD; p++)
-                if (p < a.world) v[p][u] = i < end ? a.grad[p][i] : make_int4(0, 0, 0, 0);
+                if (p < a.world) v[p][u] = i < a.slice_end ? a.grad[p][i] : zero;
         }
 #pragma unroll
         for (int u = 0; u < kU; u++) {
@@ -2190,20 +2207,22 @@ __global__ void __launch_bounds__(256) nrc_peer_reduce_kernel(const __grid_const
 #pragma unroll
             for (int p = 0; p < WORLD; p++) {
                 if (p >= a.world) break;
-                any |= (uint32_t)(v[p][u].x | v[p][u].y | v[p][u].z | v[p][u].w);
+                const uint32_t nz = (uint32_t)(v[p][u].x | v[p][u].y | v[p][u].z | v[p][u].w) & 0x7fff7fffu;
+                any |= nz;
                 const __half2* h = reinterpret_cast<const __half2*>(&v[p][u]);
 #pragma unroll
                 for (int k = 0; k < 4; k++) { const float2 f = __half22float2(h[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+                if (nz && p != a.rank && i < a.slice_end) a.grad[p][i] = zero;          // consumed: the peer's next scatter starts from zero
             }
-            if (i >= end || (any & 0x7fff7fffu) == 0) continue;            // untouched on every rank (+-0): nothing to store anywhere
+            if (i >= a.slice_end || any == 0) continue;                                 // untouched on every rank (+-0): nothing to do
             int4 r;
             __half2* o = reinterpret_cast<__half2*>(&r);
 #pragma unroll
             for (int k = 0; k < 4; k++) o[k] = __floats2half2_rn(acc[2 * k], acc[2 * k + 1]);
-            for (int p = 0; p < a.world; p++) a.grad[p][i] = r;
+            a.grad[a.rank][i] = r;                                                      // the sum stays with the owner of the slice
         }
     }
-    // ---- round B: the last block of this rank tells every rank that this rank's stores are globally visible
+    // ---- round B: the last block of this rank tells every rank that this rank no longer touches their gradient buffers
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -2213,11 +2232,177 @@ __global__ void __launch_bounds__(256) nrc_peer_reduce_kernel(const __grid_const
             for (int q = 0; q < a.world; q++) st_release_sys(a.flags[q] + kMaxPeers + a.rank, a.token);
         }
     }
+    timeline_end(a.tl, 0);
 }
 
-// the optimizer may read the summed gradients once every rank has finished storing
+// all-gather of the updated fp16 weights: the rank's slice goes to every peer.  Starts by waiting for round B (every peer has finished
+// reading this rank's gradients, i.e. the next scatter may write them) and ends with round C.
+__global__ void __maxnreg__(48) nrc_peer_publish_kernel(const __grid_constant__ PeerArgs a) {
+    timeline_begin(a.tl, 0);
+    if (threadIdx.x < a.world) while ((int32_t)(ld_acquire_sys(a.flags[a.rank] + kMaxPeers + threadIdx.x) - a.token) < 0) { }
+    __syncthreads();
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i0 = a.slice_begin + gtid; i0 < a.slice_end; i0 += stride * 4) {
+        int4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const uint64_t i = i0 + (uint64_t)u * stride; if (i < a.slice_end) v[u] = a.w16[a.rank][i]; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint64_t i = i0 + (uint64_t)u * stride;
+            if (i >= a.slice_end) break;
+            for (int p = 0; p < a.world; p++)
+                if (p != a.rank) a.w16[p][i] = v[u];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(a.done_counter, 1u) == gridDim.x - 1) {
+            *a.done_counter = 0;
+            __threadfence_system();
+            for (int q = 0; q < a.world; q++) st_release_sys(a.flags[q] + 2 * kMaxPeers + a.rank, a.token);
+        }
+    }
+    timeline_end(a.tl, 0);
+}
+
+// ONE kernel for steps 1-3 (default; the three separate kernels above remain as the step-by-step form the tests compare it with, bit for
+// bit): a warp owns a span of 32 16-byte words (128 hash-grid entries) of the rank's slice.  It loads the span from every peer's gradient
+// (NVLink latency ~2 us, hidden by the ~4 700 warps in flight), sums in rank order, clears the consumed words at their owners, compacts
+// the touched entries (ballot + popc), runs Adam on their 32-byte state records (local HBM) and stores the updated fp16 weight words
+// into its own and every peer's weight vector -- reduce-scatter, optimizer and all-gather pipelined span by span instead of three
+// bulk-synchronous phases (2 ranks: 51 + 36 + 28 us and two launch gaps -> one launch).  The first CTAs update the network weights from
+// the sum of the ranks' fp32 MLP gradients, identically on every rank.  Flag rounds: A as above; B and C collapse into one final round.
+template <int WORLD>
+__global__ void __launch_bounds__(256, 4) nrc_peer_adam_kernel(const __grid_constant__ OptArgs a, const __grid_constant__ PeerArgs pa) {
+    // spans per warp: with few ranks a thread keeps the 16-byte words of two spans in flight (the peer loads of a span are the latency
+    // that bounds the kernel: ~300 GB/s arrive per direction on this box at these message sizes, NCCL's send/recv does no better)
+    constexpr int U = WORLD <= 2 ? 2 : 1;
+    __shared__ uint32_t s_g[8][128];       // per warp: compacted summed gradients (half2 bits) of the touched entries ...
+    __shared__ uint16_t s_el[8][128];      // ... their entry index inside the warp's 128-entry span ...
+    __shared__ uint32_t s_w[8][128];       // ... and the new fp16 weights by rank
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float inv_scale = 1.0f / a.loss_scale;
+    timeline_begin(a.tl, 0);
+    // ---- round A: every rank's backward pass (and its previous EMA pass over the weights) has finished
+    if (blockIdx.x == 0 && threadIdx.x < pa.world) st_release_sys(pa.flags[threadIdx.x] + pa.rank, pa.token);
+    if (threadIdx.x < pa.world) while ((int32_t)(ld_acquire_sys(pa.flags[pa.rank] + threadIdx.x) - pa.token) < 0) { }
+    __syncthreads();
+    if (blockIdx.x < a.mlp_blocks) {
+        // ---- network weights: 64 per CTA, gradient = sum of the ranks' fp32 gradients in rank order (identical on every rank)
+        if (threadIdx.x < 64) {
+            const uint32_t i = blockIdx.x * 64 + threadIdx.x;
+            float acc = 0;
+            for (int p = 0; p < pa.world; p++) acc += pa.mlp[p][i];
+            const __half g16 = __float2half_rn(acc);                       // tcnn keeps gradients in fp16 (trainer.h:322-336)
+            float mw = a.master[i], m1 = a.m1[i], m2 = a.m2[i];
+            uint32_t st = a.steps[i];
+            const float gradient = __half2float(g16) * inv_scale + a.l2_reg * mw;
+            mw = adam_update(a, mw, m1, m2, st, gradient);
+            const __half w = __float2half_rn(mw);
+            a.master[i] = mw; a.m1[i] = m1; a.m2[i] = m2; a.steps[i] = st;
+            a.grad16[i] = g16; a.w16[i] = w;
+            const float filtered = (__half2float(a.ema16[i]) * a.ema_decay * a.ema_debias_old + __half2float(w) * (1 - a.ema_decay)) * a.ema_debias_new;
+            a.ema16[i] = __float2half_rn(filtered);
+        }
+    } else {
+        const uint32_t gb = blockIdx.x - a.mlp_blocks;
+        union V8 { int4 v; uint32_t u[4]; };
+        const int4 zero = make_int4(0, 0, 0, 0);
+        int4 v[U][WORLD];
+        V8 w[U];
+        uint64_t word[U], warp_word[U];
+        // ---- all loads of the thread first: its 16-byte word of every span, from every rank's gradient, plus the current weights
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            warp_word[u] = pa.slice_begin + ((uint64_t)gb * U + u) * 256 + warp * 32;
+            word[u] = warp_word[u] + lane;
+            const bool valid = word[u] < pa.slice_end;
+#pragma unroll
+            for (int p = 0; p < WORLD; p++)
+                if (p < pa.world) v[u][p] = valid ? pa.grad[p][word[u]] : zero;
+            w[u].v = valid ? pa.w16[pa.rank][word[u]] : zero;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (warp_word[u] >= pa.slice_end) break;                        // whole span out of range (warp-uniform)
+            const bool valid = word[u] < pa.slice_end;
+            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            uint32_t any = 0;
+#pragma unroll
+            for (int p = 0; p < WORLD; p++) {
+                if (p >= pa.world) break;
+                const uint32_t nz = (uint32_t)(v[u][p].x | v[u][p].y | v[u][p].z | v[u][p].w) & 0x7fff7fffu;
+                any |= nz;
+                const __half2* h = reinterpret_cast<const __half2*>(&v[u][p]);
+#pragma unroll
+                for (int k = 0; k < 4; k++) { const float2 f = __half22float2(h[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+                if (nz && valid) pa.grad[p][word[u]] = zero;                // consumed (own and peers'): the next scatter starts from zero
+            }
+            V8 g;
+            __half2* gh = reinterpret_cast<__half2*>(&g.v);
+#pragma unroll
+            for (int k = 0; k < 4; k++) gh[k] = __floats2half2_rn(acc[2 * k], acc[2 * k + 1]);
+            if (!any) g.v = zero;
+            uint32_t base = 0, my_rank[4];
+            bool mine[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                mine[j] = (g.u[j] & 0x7fff7fffu) != 0u;
+                const uint32_t b = __ballot_sync(0xffffffffu, mine[j]);
+                my_rank[j] = base + __popc(b & ((1u << lane) - 1));
+                base += __popc(b);
+            }
+            if (!base) continue;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (mine[j]) { s_el[warp][my_rank[j]] = (uint16_t)(lane * 4 + j); s_g[warp][my_rank[j]] = g.u[j]; }
+            __syncwarp();
+            GridAdamState* st0 = a.grid_state + warp_word[u] * 4;            // first entry of the span
+            for (uint32_t r = lane; r < base; r += 32) {
+                const uint32_t el = s_el[warp][r];
+                float4* sp = reinterpret_cast<float4*>(st0 + el);
+                float4 s0 = sp[0];                                  // master.xy, m1.xy
+                float4 s1 = sp[1];                                  // m2.xy, steps.xy
+                const uint32_t gbits = s_g[warp][r];
+                const __half2 g2 = *reinterpret_cast<const __half2*>(&gbits);
+                const float g0 = __low2float(g2), g1 = __high2float(g2);
+                uint32_t t0 = __float_as_uint(s1.z), t1 = __float_as_uint(s1.w);
+                if (g0 != 0.0f) s0.x = adam_update(a, s0.x, s0.z, s1.x, t0, g0 * inv_scale);
+                if (g1 != 0.0f) s0.y = adam_update(a, s0.y, s0.w, s1.y, t1, g1 * inv_scale);
+                s1.z = __uint_as_float(t0); s1.w = __uint_as_float(t1);
+                sp[0] = s0; sp[1] = s1;
+                s_w[warp][r] = tc05::pack_f16x2(s0.x, s0.y);
+            }
+            __syncwarp();
+            if (mine[0] | mine[1] | mine[2] | mine[3]) {
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (mine[j]) w[u].u[j] = s_w[warp][my_rank[j]];
+                for (int p = 0; p < pa.world; p++) pa.w16[p][word[u]] = w[u].v;      // all-gather of the updated word (own copy included)
+            }
+            __syncwarp();                                                            // the next span re-uses the warp's shared lists
+        }
+    }
+    // ---- final round: the last block of this rank tells every rank that its loads, clears and weight stores are globally visible
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(pa.done_counter, 1u) == gridDim.x - 1) {
+            *pa.done_counter = 0;
+            __threadfence_system();
+            for (int q = 0; q < pa.world; q++) {
+                st_release_sys(pa.flags[q] + kMaxPeers + pa.rank, pa.token);
+                st_release_sys(pa.flags[q] + 2 * kMaxPeers + pa.rank, pa.token);
+            }
+        }
+    }
+    timeline_end(a.tl, 0);
+}
+
+// the next forward pass may gather the weights once every rank's slice has landed (round C)
 __global__ void nrc_peer_wait_kernel(const uint32_t* flags, int world, uint32_t token) {
-    if ((int)threadIdx.x < world) while ((int32_t)(ld_acquire_sys(flags + kMaxPeers + threadIdx.x) - token) < 0) { }
+    if ((int)threadIdx.x < world) while ((int32_t)(ld_acquire_sys(flags + 2 * kMaxPeers + threadIdx.x) - token) < 0) { }
 }
 
 }  // namespace nrchpm

@@ -1,6 +1,7 @@
-"""GPU, needs >= 2 devices on one node (skipped otherwise): the data-parallel gradient exchange through peer memory
-(nrc_peer_exchange / nrc_peer_reduce_kernel) equals an NCCL all-reduce of the same gradients bit for bit, every rank ends up with
-the identical buffer, and replicas that exchange every step stay bit-identical (scripts/check_peer_exchange.py under torchrun)."""
+"""GPU, needs >= 2 devices on one node (skipped otherwise): the sharded data-parallel optimizer step through peer memory
+(nrc_peer_exchange -> nrc_optimizer_step: reduce-scatter, Adam on the rank's slice, weight all-gather) -- every rank's slice of the
+summed gradient equals an NCCL all-reduce of the same gradients bit for bit, consumed peer words are cleared, and replicas stay
+bit-identical (scripts/check_peer_exchange.py under torchrun)."""
 import os
 import socket
 import subprocess
@@ -26,4 +27,5 @@ def test_peer_exchange_matches_nccl_world2():
            os.path.join(ROOT, "scripts", "check_peer_exchange.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
-    assert '"peer_equals_nccl_sum_bitwise": true' in res.stdout and '"replicas_bit_identical": true' in res.stdout
+    assert '"own_slice_equals_nccl_sum_bitwise": true' in res.stdout and '"replicas_bit_identical": true' in res.stdout
+    assert '"fused_kernel_equals_step_by_step_bitwise": true' in res.stdout
