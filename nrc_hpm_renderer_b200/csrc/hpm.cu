@@ -158,6 +158,7 @@ void Renderer::pass_prep_train(const float fr[4]) {
         a.train_ray = train_ray_.ptr; a.train_flags = train_flags_.ptr; a.ring = ring_.ptr;
         a.block_totals = block_totals_.ptr; a.n_blocks = n_blocks;
         a.train_in = cur_train_in(); a.train_target = cur_train_target(); a.lookups = counters_.ptr + 1;
+        last_train_set_ = train_set_;
         if (a.sc.maj) hpm_train_trace_kernel<true><<<(n_train_ + 127) / 128, 128, 0, stream_>>>(a);
         else hpm_train_trace_kernel<false><<<(n_train_ + 127) / 128, 128, 0, stream_>>>(a);
         check_launch("hpm_train_trace_kernel");
@@ -247,8 +248,8 @@ void Renderer::buffer_info(int which, void** ptr, size_t* bytes) {
         case HPM_BUF_NRC_DIR: p = dir_.ptr; b = dir_.bytes(); break;
         case HPM_BUF_INFER_INPUT: p = infer_in_.ptr; b = infer_in_.bytes(); break;
         case HPM_BUF_INFER_OUTPUT: p = infer_out_.ptr; b = infer_out_.bytes(); break;
-        case HPM_BUF_TRAIN_INPUT: p = cur_train_in(); b = train_in_.bytes(); break;          // the set written last
-        case HPM_BUF_TRAIN_TARGET: p = cur_train_target(); b = train_target_.bytes(); break;
+        case HPM_BUF_TRAIN_INPUT: p = last_train_in(); b = train_in_.bytes(); break;          // the set written last (not the one the next frame will write)
+        case HPM_BUF_TRAIN_TARGET: p = last_train_target(); b = train_target_.bytes(); break;
         case HPM_BUF_TRAIN_RING: p = ring_.ptr; b = ring_.bytes(); break;
         case HPM_BUF_INFER_FILTER: p = filter_.ptr; b = filter_.bytes(); break;
         case HPM_BUF_COUNTERS: p = counters_.ptr; b = counters_.bytes(); break;
@@ -263,6 +264,7 @@ void Renderer::read_buffer(int which, void* host, size_t bytes) {
     buffer_info(which, &p, &b);
     NRCHPM_REQUIRE(bytes <= b, "hpm_read_buffer: size exceeds the buffer");
     NRCHPM_CUDA(cudaStreamSynchronize(stream_));
+    if (train_stream_) NRCHPM_CUDA(cudaStreamSynchronize(train_stream_));     // a queued Train() still reads / the cache still writes behind the main stream
     if (which == HPM_BUF_COUNTERS) {
         // counters[2] mirrors the device-side active record count
         uint32_t cnt = 0;

@@ -57,9 +57,12 @@ private:
     cudaStream_t train_stream_ = nullptr;
     cudaEvent_t ev_infer_done_ = nullptr, ev_train_done_ = nullptr;
     bool train_in_flight_ = false;
-    int train_set_ = 0;
+    int train_set_ = 0;              // record set the NEXT prep_train pass writes (pipelined training double-buffers the records)
+    int last_train_set_ = 0;         // record set the LAST prep_train pass wrote: what hpm_buffer_info / hpm_read_buffer expose
     float* cur_train_in() { return train_set_ ? train_in2_.ptr : train_in_.ptr; }
     float* cur_train_target() { return train_set_ ? train_target2_.ptr : train_target_.ptr; }
+    float* last_train_in() { return last_train_set_ ? train_in2_.ptr : train_in_.ptr; }
+    float* last_train_target() { return last_train_set_ ? train_target2_.ptr : train_target_.ptr; }
     DeviceBuffer<uint32_t> ring_, filter_, active_list_, active_count_, train_flags_, block_totals_;
     DeviceBuffer<unsigned long long> counters_;
     uint32_t* filter_host_ = nullptr;     // pinned

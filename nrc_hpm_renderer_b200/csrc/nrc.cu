@@ -360,11 +360,15 @@ void NrcCache::setup_kernels() {
             NRCHPM_CUDA(cudaFuncSetAttribute(nrc_train_fused_kernel<IN_W, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train_smem_bytes<IN_W>(H)));
         }
     });
+    NRCHPM_CUDA(cudaFuncSetAttribute(nrc_peer_adam_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)peer_adam_smem_bytes<2>()));
+    NRCHPM_CUDA(cudaFuncSetAttribute(nrc_peer_adam_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)peer_adam_smem_bytes<4>()));
+    NRCHPM_CUDA(cudaFuncSetAttribute(nrc_peer_adam_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)peer_adam_smem_bytes<8>()));
     // tuning knobs (experiments only; the defaults are the measured best)
     if (const char* v = std::getenv("NRCHPM_INFER_GROUPS")) infer_groups_ = std::max(0, std::min(3, std::atoi(v)));
     if (const char* v = std::getenv("NRCHPM_TRAIN_GROUPS")) train_groups_ = std::max(0, std::min(1, std::atoi(v)));
     if (const char* v = std::getenv("NRCHPM_INFER_WS")) infer_ws_ = std::atoi(v) != 0 ? 1 : 0;   // 0: tile-per-warpgroup kernel
     if (const char* v = std::getenv("NRCHPM_OVERLAP")) overlap_schedule_ = std::atoi(v) != 0;          // data-parallel replicas: 0 = serial Inference() -> Train()
+    if (const char* v = std::getenv("NRCHPM_OVERLAP_SMS")) overlap_infer_sms_ = (uint32_t)std::max(1, std::atoi(v));
     if (const char* v = std::getenv("NRCHPM_OVERLAP_HEAD")) overlap_head_ = std::max(0.0, std::min(1.0, std::atof(v)));
     if (const char* v = std::getenv("NRCHPM_PEER_FUSED")) peer_fused_ = std::atoi(v) != 0;             // 0: gather / Adam / publish as three kernels
     if (const char* v = std::getenv("NRCHPM_PEER_CTAS")) peer_ctas_ = (uint32_t)std::max(1, std::atoi(v));
@@ -609,8 +613,11 @@ void NrcCache::optimizer_step(cudaStream_t s) {
         PeerArgs pa{};
         fill_peer_args(pa);
         cudaLaunchConfig_t cfg = {};
-        const unsigned spans_per_cta = peer_world_ <= 2 ? 2u : 1u;       // nrc_peer_adam_kernel: U spans per warp
-        cfg.gridDim = a.mlp_blocks + (grid_blocks + spans_per_cta - 1) / spans_per_cta; cfg.blockDim = 256; cfg.stream = s;
+        // persistent grid over the slice's blocks of 256 words; shared memory (the cp.async ring) bounds the CTAs per SM
+        const size_t smem = peer_world_ <= 2 ? peer_adam_smem_bytes<2>() : peer_world_ <= 4 ? peer_adam_smem_bytes<4>() : peer_adam_smem_bytes<8>();
+        const unsigned per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smem + 12 * 1024)));
+        const unsigned peer_grid = std::min<unsigned>(grid_blocks, (peer_ctas_ ? peer_ctas_ : (unsigned)sm_count_ * per_sm));
+        cfg.gridDim = a.mlp_blocks + peer_grid; cfg.blockDim = 256; cfg.stream = s; cfg.dynamicSmemBytes = smem;
         cudaLaunchAttribute attr[1];
         if (l2_window_bytes_) {
             attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
@@ -826,7 +833,10 @@ void NrcCache::infer_and_train_overlapped() {
         peer_exchange(st);
         NRCHPM_CUDA(cudaStreamWaitEvent(si, ev_bwd, 0));
         const uint32_t m = b + 1 < nb ? std::min(chunk, n - off) : n - off;
-        if (m) inference_with(infer_snapshot_.ptr, infer_in_ + 5 * (size_t)off, infer_out_ + 3 * (size_t)off, m, nullptr, nullptr, si, 0);
+        // the chunk takes `overlap_infer_sms_` SMs (one persistent CTA each, dispatched first: its stream is released by the backward pass,
+        // the peer kernel follows a small reduction kernel); the peer kernel's CTAs cannot share an SM with an inference CTA (registers)
+        // and fill the remaining SMs, where they keep the NVLink loads of ~4 CTAs per SM in flight
+        if (m) inference_with(infer_snapshot_.ptr, infer_in_ + 5 * (size_t)off, infer_out_ + 3 * (size_t)off, m, nullptr, nullptr, si, overlap_infer_sms_);
         off += m;
         NRCHPM_CUDA(cudaEventRecord(ev_chunk, si));
         // the exchange kernels (one 48-register CTA per SM) and the optimizer on this rank's slice (small CTAs) share the SMs with the

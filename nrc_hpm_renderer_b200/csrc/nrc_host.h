@@ -145,7 +145,7 @@ private:
     cudaStream_t ov_inf_stream_ = nullptr, ov_tr_stream_ = nullptr;
     cudaEvent_t ov_ev_[5 + 2 * kMaxOverlapBatches] = {};
     cudaEvent_t ema_gate_ = nullptr;
-    bool overlap_schedule_ = false, peer_one_cta_per_sm_ = false; double overlap_head_ = 0.0; uint32_t peer_ctas_ = 0;
+    bool overlap_schedule_ = true, peer_one_cta_per_sm_ = false; double overlap_head_ = 0.0; uint32_t peer_ctas_ = 0, overlap_infer_sms_ = 112;
     int peer_rank_ = -1, peer_world_ = 0;
     uint32_t peer_token_ = 0;
     bool peer_fused_ = true;                         // reduce-scatter + Adam + weight all-gather as one kernel (nrc_peer_adam_kernel)

@@ -2267,17 +2267,24 @@ __global__ void __maxnreg__(48) nrc_peer_publish_kernel(const __grid_constant__ 
 }
 
 // ONE kernel for steps 1-3 (default; the three separate kernels above remain as the step-by-step form the tests compare it with, bit for
-// bit): a warp owns a span of 32 16-byte words (128 hash-grid entries) of the rank's slice.  It loads the span from every peer's gradient
-// (NVLink latency ~2 us, hidden by the ~4 700 warps in flight), sums in rank order, clears the consumed words at their owners, compacts
+// bit): a warp owns a span of 32 16-byte words (128 hash-grid entries) of the rank's slice.  It receives the span from every peer's
+// gradient, sums in rank order, clears the consumed words at their owners, compacts
 // the touched entries (ballot + popc), runs Adam on their 32-byte state records (local HBM) and stores the updated fp16 weight words
 // into its own and every peer's weight vector -- reduce-scatter, optimizer and all-gather pipelined span by span instead of three
 // bulk-synchronous phases (2 ranks: 51 + 36 + 28 us and two launch gaps -> one launch).  The first CTAs update the network weights from
 // the sum of the ranks' fp32 MLP gradients, identically on every rank.  Flag rounds: A as above; B and C collapse into one final round.
+// The peer loads are the latency that bounds the kernel (NVLink round trip ~2 us idle, ~10 us loaded; ~300 GB/s arrive per direction on
+// this box at these message sizes, NCCL's send / recv does no better), and registers bound how many loads a thread can keep in flight.
+// So the gradient words travel with cp.async (LDGSTS: peer HBM -> this SM's shared memory, no register staging): a persistent CTA
+// works through blocks of 256 words and keeps DEPTH - 1 blocks of every peer in flight; each thread only ever reads the slots it
+// filled itself, so cp.async.wait_group is the only synchronisation of the pipeline.
+template <int WORLD> __host__ __device__ constexpr int peer_adam_depth() { return WORLD <= 2 ? 4 : WORLD <= 4 ? 3 : 2; }
+template <int WORLD> __host__ __device__ constexpr size_t peer_adam_smem_bytes() { return (size_t)peer_adam_depth<WORLD>() * WORLD * 256 * sizeof(int4); }
+
 template <int WORLD>
-__global__ void __launch_bounds__(256, 4) nrc_peer_adam_kernel(const __grid_constant__ OptArgs a, const __grid_constant__ PeerArgs pa) {
-    // spans per warp: with few ranks a thread keeps the 16-byte words of two spans in flight (the peer loads of a span are the latency
-    // that bounds the kernel: ~300 GB/s arrive per direction on this box at these message sizes, NCCL's send/recv does no better)
-    constexpr int U = WORLD <= 2 ? 2 : 1;
+__global__ void __launch_bounds__(256) nrc_peer_adam_kernel(const __grid_constant__ OptArgs a, const __grid_constant__ PeerArgs pa) {
+    constexpr int DEPTH = peer_adam_depth<WORLD>();
+    extern __shared__ __align__(16) int4 stage[];          // [DEPTH][WORLD][256]
     __shared__ uint32_t s_g[8][128];       // per warp: compacted summed gradients (half2 bits) of the touched entries ...
     __shared__ uint16_t s_el[8][128];      // ... their entry index inside the warp's 128-entry span ...
     __shared__ uint32_t s_w[8][128];       // ... and the new fp16 weights by rank
@@ -2306,38 +2313,43 @@ __global__ void __launch_bounds__(256, 4) nrc_peer_adam_kernel(const __grid_cons
             a.ema16[i] = __float2half_rn(filtered);
         }
     } else {
-        const uint32_t gb = blockIdx.x - a.mlp_blocks;
+        const uint64_t gb = blockIdx.x - a.mlp_blocks, n_ctas = gridDim.x - a.mlp_blocks;
+        const uint64_t n_blocks = (pa.slice_end - pa.slice_begin + 255) / 256;
         union V8 { int4 v; uint32_t u[4]; };
         const int4 zero = make_int4(0, 0, 0, 0);
-        int4 v[U][WORLD];
-        V8 w[U];
-        uint64_t word[U], warp_word[U];
-        // ---- all loads of the thread first: its 16-byte word of every span, from every rank's gradient, plus the current weights
+        auto issue = [&](uint64_t blk, int buf) {           // this thread's word of block `blk`, from every rank's gradient -> its own slots
+            if (blk < n_blocks) {
+                const uint64_t wd = min(pa.slice_begin + blk * 256 + threadIdx.x, pa.slice_end - 1);
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            warp_word[u] = pa.slice_begin + ((uint64_t)gb * U + u) * 256 + warp * 32;
-            word[u] = warp_word[u] + lane;
-            const bool valid = word[u] < pa.slice_end;
+                for (int p = 0; p < WORLD; p++)
+                    if (p < pa.world) tc05::cp_async16(&stage[(buf * WORLD + p) * 256 + threadIdx.x], &pa.grad[p][wd]);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
 #pragma unroll
-            for (int p = 0; p < WORLD; p++)
-                if (p < pa.world) v[u][p] = valid ? pa.grad[p][word[u]] : zero;
-            w[u].v = valid ? pa.w16[pa.rank][word[u]] : zero;
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (warp_word[u] >= pa.slice_end) break;                        // whole span out of range (warp-uniform)
-            const bool valid = word[u] < pa.slice_end;
+        for (int d = 0; d < DEPTH - 1; d++) issue(gb + d * n_ctas, d);
+        uint32_t it = 0;
+        for (uint64_t blk = gb; blk < n_blocks; blk += n_ctas, it++) {
+            issue(blk + (DEPTH - 1) * n_ctas, (it + DEPTH - 1) % DEPTH);
+            asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
+            const int buf = it % DEPTH;
+            const uint64_t warp_word = pa.slice_begin + blk * 256 + warp * 32, word = warp_word + lane;
+            if (warp_word >= pa.slice_end) continue;                          // whole span out of range (warp-uniform)
+            const bool valid = word < pa.slice_end;
+            V8 w;
+            w.v = valid ? pa.w16[pa.rank][word] : zero;
             float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             uint32_t any = 0;
 #pragma unroll
             for (int p = 0; p < WORLD; p++) {
                 if (p >= pa.world) break;
-                const uint32_t nz = (uint32_t)(v[u][p].x | v[u][p].y | v[u][p].z | v[u][p].w) & 0x7fff7fffu;
+                const int4 v = valid ? stage[(buf * WORLD + p) * 256 + threadIdx.x] : zero;
+                const uint32_t nz = (uint32_t)(v.x | v.y | v.z | v.w) & 0x7fff7fffu;
                 any |= nz;
-                const __half2* h = reinterpret_cast<const __half2*>(&v[u][p]);
+                const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
                 for (int k = 0; k < 4; k++) { const float2 f = __half22float2(h[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
-                if (nz && valid) pa.grad[p][word[u]] = zero;                // consumed (own and peers'): the next scatter starts from zero
+                if (nz) pa.grad[p][word] = zero;                            // consumed (own and peers'): the next scatter starts from zero
             }
             V8 g;
             __half2* gh = reinterpret_cast<__half2*>(&g.v);
@@ -2358,7 +2370,7 @@ __global__ void __launch_bounds__(256, 4) nrc_peer_adam_kernel(const __grid_cons
             for (int j = 0; j < 4; j++)
                 if (mine[j]) { s_el[warp][my_rank[j]] = (uint16_t)(lane * 4 + j); s_g[warp][my_rank[j]] = g.u[j]; }
             __syncwarp();
-            GridAdamState* st0 = a.grid_state + warp_word[u] * 4;            // first entry of the span
+            GridAdamState* st0 = a.grid_state + warp_word * 4;               // first entry of the span
             for (uint32_t r = lane; r < base; r += 32) {
                 const uint32_t el = s_el[warp][r];
                 float4* sp = reinterpret_cast<float4*>(st0 + el);
@@ -2378,11 +2390,12 @@ __global__ void __launch_bounds__(256, 4) nrc_peer_adam_kernel(const __grid_cons
             if (mine[0] | mine[1] | mine[2] | mine[3]) {
 #pragma unroll
                 for (int j = 0; j < 4; j++)
-                    if (mine[j]) w[u].u[j] = s_w[warp][my_rank[j]];
-                for (int p = 0; p < pa.world; p++) pa.w16[p][word[u]] = w[u].v;      // all-gather of the updated word (own copy included)
+                    if (mine[j]) w.u[j] = s_w[warp][my_rank[j]];
+                for (int p = 0; p < pa.world; p++) pa.w16[p][word] = w.v;      // all-gather of the updated word (own copy included)
             }
-            __syncwarp();                                                            // the next span re-uses the warp's shared lists
+            __syncwarp();                                                      // the next block re-uses the warp's shared lists
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
     }
     // ---- final round: the last block of this rank tells every rank that its loads, clears and weight stores are globally visible
     __threadfence_system();

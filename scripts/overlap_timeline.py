@@ -33,9 +33,13 @@ k = _lib.lib().nrc_debug_timeline(nrc._h, tl.ctypes.data_as(C.c_void_p), 256)
 if rank == 0:
     t = tl[:2 * k].astype(np.float64).reshape(k, 2); t = (t - t[:, 0].min()) / 1e3
     fused = os.environ.get("NRCHPM_PEER_FUSED", "1") != "0"
-    overlap = os.environ.get("NRCHPM_OVERLAP", "0") != "0"
-    per_batch = ["fused", "peer_adam", "ema"] if fused else (["fused", "gather", "infer_chunk", "adam", "ema", "publish"] if overlap else ["fused", "gather", "adam", "ema", "publish"])
-    names = ([] if (overlap and not fused) else ["inference"]) + per_batch * TRAIN_BATCHES
+    overlap = os.environ.get("NRCHPM_OVERLAP", "1") != "0"
+    if fused and overlap: per_batch, lead = ["fused", "infer_chunk", "peer_adam", "ema"], []
+    elif fused: per_batch, lead = ["fused", "peer_adam", "ema"], ["inference"]
+    elif overlap: per_batch, lead = ["fused", "gather", "infer_chunk", "adam", "ema", "publish"], []
+    else: per_batch, lead = ["fused", "gather", "adam", "ema", "publish"], ["inference"]
+    if overlap and float(os.environ.get("NRCHPM_OVERLAP_HEAD", "0")) > 0: lead = ["infer_head"]
+    names = lead + per_batch * TRAIN_BATCHES
     per = len(names)
     for j, (b, e) in enumerate(t):
         print(f"{names[j % per]:12s} {b:9.1f} {e:9.1f}  ({e - b:7.1f} us)")
