@@ -20,20 +20,29 @@ static thread_local std::string t_last_error;
 void set_last_error(const std::string& msg) { t_last_error = msg; }
 
 // launch of a training-path kernel with the access-policy window that keeps [grad16 | w16] in the persisting part of L2
+// `pdl`: programmatic dependent launch -- the kernel may be dispatched while the kernel before it on the stream drains; it orders
+// itself behind that kernel with griddepcontrol.wait (pdl_wait) before it touches anything the kernel wrote
 template <class K, class A>
-void NrcCache::launch_hot(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t s, const A& args) {
+void NrcCache::launch_hot(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t s, const A& args, bool pdl) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
+    unsigned n = 0;
     if (l2_window_bytes_) {
-        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-        attr[0].val.accessPolicyWindow.base_ptr = hot_.ptr;
-        attr[0].val.accessPolicyWindow.num_bytes = l2_window_bytes_;
-        attr[0].val.accessPolicyWindow.hitRatio = l2_hit_ratio_;
-        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        cfg.attrs = attr; cfg.numAttrs = 1;
+        attr[n].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[n].val.accessPolicyWindow.base_ptr = hot_.ptr;
+        attr[n].val.accessPolicyWindow.num_bytes = l2_window_bytes_;
+        attr[n].val.accessPolicyWindow.hitRatio = l2_hit_ratio_;
+        attr[n].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[n].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        n++;
     }
+    if (pdl && pdl_enabled_) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        n++;
+    }
+    if (n) { cfg.attrs = attr; cfg.numAttrs = n; }
     NRCHPM_CUDA(cudaLaunchKernelEx(&cfg, kernel, args));
 }
 
@@ -365,6 +374,7 @@ void NrcCache::setup_kernels() {
     NRCHPM_CUDA(cudaFuncSetAttribute(nrc_peer_adam_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)peer_adam_smem_bytes<8>()));
     // tuning knobs (experiments only; the defaults are the measured best)
     if (const char* v = std::getenv("NRCHPM_INFER_GROUPS")) infer_groups_ = std::max(0, std::min(3, std::atoi(v)));
+    if (const char* v = std::getenv("NRCHPM_PDL")) pdl_enabled_ = std::atoi(v) != 0;                   // programmatic dependent launch of the training chain
     if (const char* v = std::getenv("NRCHPM_TRAIN_GROUPS")) train_groups_ = std::max(0, std::min(1, std::atoi(v)));
     if (const char* v = std::getenv("NRCHPM_INFER_WS")) infer_ws_ = std::atoi(v) != 0 ? 1 : 0;   // 0: tile-per-warpgroup kernel
     if (const char* v = std::getenv("NRCHPM_OVERLAP")) overlap_schedule_ = std::atoi(v) != 0;          // data-parallel replicas: 0 = serial Inference() -> Train()
@@ -505,8 +515,8 @@ void NrcCache::training_step(const float* d_in, const float* d_target, uint32_t 
         a.prof = train_prof_.ptr;
         a.tl = timeline_slot();
         const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t)sm_count_);
-        if (train_tpr_ == 4) { NRC_DISPATCH_INW(enc_.in_w, { launch_hot(nrc_train_fused_kernel<IN_W, 4>, grid, 512, train_smem_bytes<IN_W>(H), s, a); }); }
-        else { NRC_DISPATCH_INW(enc_.in_w, { launch_hot(nrc_train_fused_kernel<IN_W, 2>, grid, 256, train_smem_bytes<IN_W>(H), s, a); }); }
+        if (train_tpr_ == 4) { NRC_DISPATCH_INW(enc_.in_w, { launch_hot(nrc_train_fused_kernel<IN_W, 4>, grid, 512, train_smem_bytes<IN_W>(H), s, a, true); }); }
+        else { NRC_DISPATCH_INW(enc_.in_w, { launch_hot(nrc_train_fused_kernel<IN_W, 2>, grid, 256, train_smem_bytes<IN_W>(H), s, a, true); }); }
         check_launch("nrc_train_fused_kernel");
         dw_chunks_ = grid;
         grid_grad_dirty_ = n_grid_ != 0;
@@ -633,12 +643,14 @@ void NrcCache::optimizer_step(cudaStream_t s) {
         nrc_peer_wait_kernel<<<1, 32, 0, s>>>(peer_flag_words_.ptr, peer_world_, pa.token);
         check_launch("nrc_peer_wait_kernel");
     } else {
-        launch_hot(nrc_adam_kernel, a.mlp_blocks + grid_blocks, 256, 0, s, a);
+        launch_hot(nrc_adam_kernel, a.mlp_blocks + grid_blocks, 256, 0, s, a, true);
         check_launch("nrc_adam_kernel");
         if (sharded) peer_publish(s);   // ... and receives everybody else's
     }
     if (has_grid) {
-        // ---- the dense EMA of the hash-grid weights, which only Inference() reads: side stream, underneath the next step
+        // ---- the dense EMA of the hash-grid weights, which only Inference() reads: side stream, underneath the next step.  (Round 2 also
+        // measured it as extra CTAs of the next training launch, on the 20 SMs a 2^14 batch leaves idle: 20 SMs stream the 85 MB in
+        // 85 us, longer than the training CTAs' 48 us -- 1.08 instead of 0.98 ms per bench step.)
         NRCHPM_CUDA(cudaEventRecord(adam_done_, s));
         NRCHPM_CUDA(cudaStreamWaitEvent(ema_stream_, adam_done_, 0));
         if (ema_gate_) { NRCHPM_CUDA(cudaStreamWaitEvent(ema_stream_, ema_gate_, 0)); ema_gate_ = nullptr; }   // a snapshot copy still reads the EMA weights
@@ -651,7 +663,7 @@ void NrcCache::optimizer_step(cudaStream_t s) {
     grads_pending_ = false;
 }
 
-// the EMA weights are complete once the last nrc_grid_ema_kernel has finished: every reader of ema16_ orders itself behind it
+// the EMA weights are complete once the last EMA pass has finished: every reader of ema16_ orders itself behind it
 void NrcCache::wait_ema(cudaStream_t s) {
     if (ema_in_flight_) NRCHPM_CUDA(cudaStreamWaitEvent(s, ema_done_, 0));
 }

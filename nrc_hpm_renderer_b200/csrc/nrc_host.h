@@ -106,7 +106,7 @@ private:
     DeviceBuffer<__half> hot_;
     HalfView w16_, grad16_;
     size_t l2_window_bytes_ = 0; float l2_hit_ratio_ = 1.0f;
-    template <class K, class A> void launch_hot(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t s, const A& args);
+    template <class K, class A> void launch_hot(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t s, const A& args, bool pdl = false);
     DeviceBuffer<__half> ema16_, x16_, acts_, dacts_, out16_, dout16_, dx16_;
     DeviceBuffer<uint32_t> steps_;
     DeviceBuffer<GridAdamState> grid_state_;       // Adam state of the encoding parameters, one 32-byte record per entry
@@ -129,6 +129,7 @@ private:
     cudaStream_t ema_stream_ = nullptr;              // dense EMA pass of the encoding weights, underneath the next training step
     cudaEvent_t adam_done_ = nullptr, ema_done_ = nullptr;
     bool ema_in_flight_ = false;
+    bool pdl_enabled_ = true;                        // programmatic dependent launch of the training chain (NRCHPM_PDL=0 disables)
     void wait_ema(cudaStream_t s);
     // en::NeuralRadianceCache::Init state
     uint32_t infer_count_ = 0;

@@ -465,6 +465,12 @@ __global__ void __launch_bounds__(128) nrc_encode_kernel(const __grid_constant__
 // ---------------------------------------------------------------------------------------------- helpers
 // development aid (NRCHPM_TRAIN_PROF=1): device-side timeline of a training step, tl[2k] = earliest start, tl[2k+1] = latest end of kernel k
 __device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// programmatic dependent launch (PTX griddepcontrol): `pdl_wait` returns once the kernel launched before this one on the stream has
+// completed and its memory is visible (no-op when the launch did not carry cudaLaunchAttributeProgrammaticStreamSerialization);
+// `pdl_trigger` lets the next kernel's CTAs be dispatched as soon as every CTA of this grid has called it or exited, so the dependent's
+// launch latency and prologue (TMEM allocation, barrier init) run underneath this kernel's tail
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void timeline_begin(unsigned long long* tl, int k) { if (tl && threadIdx.x == 0) atomicMin(tl + 2 * k, global_ns()); }
 __device__ __forceinline__ void timeline_end(unsigned long long* tl, int k) { if (tl && threadIdx.x == 0) atomicMax(tl + 2 * k + 1, global_ns()); }
 
@@ -1593,6 +1599,31 @@ struct TrainArgs {
     long long* prof;            // optional [gridDim.x][16] phase time stamps (clock64 of thread 0), development aid
     unsigned long long* tl;     // optional device-side timeline (development aid)
 };
+
+// dense EMA of the hash-grid part of the fp16 weight vector (ema.h:63-76): grid-stride loop over 16-byte words, four words of each
+// array in flight per thread
+__device__ __forceinline__ void grid_ema_pass(const __half* w16, __half* ema16, uint64_t n_vec, float decay, float debias_old, float debias_new,
+                                              uint64_t first, uint64_t stride) {
+    const int4* wv = reinterpret_cast<const int4*>(w16);
+    int4* ev = reinterpret_cast<int4*>(ema16);
+    for (uint64_t v0 = first; v0 < n_vec; v0 += 4 * stride) {
+        union V8 { int4 v; __half h[8]; };
+        V8 w[4], e[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint64_t v = v0 + u * stride;
+            if (v < n_vec) { w[u].v = wv[v]; e[u].v = ev[v]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint64_t v = v0 + u * stride;
+            if (v >= n_vec) break;
+#pragma unroll
+            for (int j = 0; j < 8; j++) e[u].h[j] = __float2half_rn((__half2float(e[u].h[j]) * decay * debias_old + __half2float(w[u].h[j]) * (1 - decay)) * debias_new);
+            ev[v] = e[u].v;
+        }
+    }
+}
 #define NRC_PROF(k) do { if (a.prof && tid == 0) a.prof[(size_t)blockIdx.x * 16 + (k)] = clock64(); } while (0)
 
 template <int IN_W>
@@ -1634,9 +1665,13 @@ __global__ void __launch_bounds__(128 * TPR, 1) nrc_train_fused_kernel(const __g
     uint8_t* do_s = dy_s + 2 * 16384;
 
     NRC_PROF(0);
-    timeline_begin(a.tl, 0);
     if (warp == 0) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
     if (tid == 0) { mbar_init(&bar_mma, 1); mbar_init(&bar_dw[0], 1); mbar_init(&bar_dw[1], 1); mbar_init(&wbar, NT); fence_mbar_init(); }
+    // everything above ran underneath the tail of the optimizer kernel launched before (programmatic dependent launch); the weights
+    // it wrote are read from here on
+    pdl_wait();
+    pdl_trigger();          // the optimizer kernel that follows may be dispatched (its CTAs wait for this grid at their own pdl_wait)
+    timeline_begin(a.tl, 0);
     // the weights travel to shared memory while the first tile is encoded (see nrc_forward2_kernel)
     copy_weights_kmajor_async(w0_s, a.params, kWidth, IN_W, tid, NT);
     for (int l = 1; l < H; l++) copy_weights_kmajor_async(wh_s + (l - 1) * 8192, a.params + IN_W * kWidth + (l - 1) * kWidth * kWidth, kWidth, kWidth, tid, NT);
@@ -2017,6 +2052,8 @@ __global__ void __launch_bounds__(256, NRC_OPT_MIN_BLOCKS) nrc_adam_kernel(const
     __shared__ uint16_t s_el[8][128];      // ... and their entry index inside the warp's 128-entry span
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float inv_scale = 1.0f / a.loss_scale;
+    pdl_wait();             // the gradients of the training kernel launched before (programmatic dependent launch)
+    pdl_trigger();          // the next training kernel's CTAs may be dispatched as this grid drains; they wait for its completion themselves
     timeline_begin(a.tl, 0);
     if (blockIdx.x < a.mlp_blocks) {
         // ---- network weights: 64 per CTA; four thread groups add a quarter of the partials each, in chunk order (deterministic)
@@ -2100,27 +2137,9 @@ __global__ void __launch_bounds__(256, NRC_OPT_MIN_BLOCKS) nrc_adam_kernel(const
 // dense EMA of the hash-grid part of the fp16 weight vector (ema.h:63-76): persistent grid-stride loop, four 16-byte vectors of each
 // array in flight per thread
 __global__ void __launch_bounds__(256) nrc_grid_ema_kernel(const __grid_constant__ OptArgs a) {
-    const uint64_t n_vec = (a.n_params - a.n_mlp) / 8, stride = (uint64_t)gridDim.x * 256;
-    int4* wv = reinterpret_cast<int4*>(a.w16 + a.n_mlp);
-    int4* ev = reinterpret_cast<int4*>(a.ema16 + a.n_mlp);
     timeline_begin(a.tl_ema, 0);
-    for (uint64_t v0 = (uint64_t)blockIdx.x * 256 + threadIdx.x; v0 < n_vec; v0 += 4 * stride) {
-        union V8 { int4 v; __half h[8]; };
-        V8 w[4], e[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const uint64_t v = v0 + u * stride;
-            if (v < n_vec) { w[u].v = wv[v]; e[u].v = ev[v]; }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const uint64_t v = v0 + u * stride;
-            if (v >= n_vec) break;
-#pragma unroll
-            for (int j = 0; j < 8; j++) e[u].h[j] = __float2half_rn((__half2float(e[u].h[j]) * a.ema_decay * a.ema_debias_old + __half2float(w[u].h[j]) * (1 - a.ema_decay)) * a.ema_debias_new);
-            ev[v] = e[u].v;
-        }
-    }
+    grid_ema_pass(a.w16 + a.n_mlp, a.ema16 + a.n_mlp, (a.n_params - a.n_mlp) / 8, a.ema_decay, a.ema_debias_old, a.ema_debias_new,
+                  (uint64_t)blockIdx.x * 256 + threadIdx.x, (uint64_t)gridDim.x * 256);
     timeline_end(a.tl_ema, 0);
 }
 

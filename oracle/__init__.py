@@ -69,6 +69,7 @@ def _declare(l):
     l.hpmo_rng_stream.argtypes = [C.c_float, C.c_float, fp, C.c_int, fp]
     l.hpmo_gen_rays.restype = C.c_uint64
     l.hpmo_gen_rays.argtypes = [C.POINTER(HpmoScene), C.POINTER(HpmoConfig), C.POINTER(HpmoCamera), fp, fp, fp, fp, fp]
+    l.hpmo_primary_hit.argtypes = [C.POINTER(HpmoScene), C.POINTER(HpmoConfig), C.POINTER(HpmoCamera), C.POINTER(C.c_uint8)]
     l.hpmo_prep_infer.argtypes = [C.POINTER(HpmoScene), C.POINTER(HpmoConfig), fp, fp, fp, fp, C.POINTER(C.c_uint32)]
     l.hpmo_prep_train.restype = C.c_uint64
     l.hpmo_prep_train.argtypes = [C.POINTER(HpmoScene), C.POINTER(HpmoConfig), fp, fp, fp, fp, C.POINTER(C.c_uint32), fp, fp]
@@ -143,6 +144,13 @@ def gen_rays(scene, cfg, cam, frame_random):
     fr = np.asarray(frame_random, dtype=np.float32)
     lookups = lib().hpmo_gen_rays(C.byref(scene), C.byref(cfg), C.byref(cam), _fp(fr), _fp(color), _fp(info), _fp(org), _fp(dr))
     return dict(color=color, info=info, origin=org, dir=dr, lookups=int(lookups))
+
+
+def primary_hit(scene, cfg, cam) -> np.ndarray:
+    """per pixel [H][W]: 1 when the shader's FindEntryExit march reaches the volume, 0 for a sky pixel (gen_rays.comp:73-80)"""
+    hit = np.zeros((cfg.height, cfg.width), np.uint8)
+    lib().hpmo_primary_hit(C.byref(scene), C.byref(cfg), C.byref(cam), hit.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return hit
 
 
 def prep_infer(scene, cfg, rays):

@@ -269,6 +269,31 @@ void hpmo_rng_stream(float u, float v, const float frame_random[4], int n, float
     for (int i = 0; i < n; i++) out[i] = c.rand_float(1.0f);
 }
 
+// gen_rays.comp:73-80 only: per pixel, 1 when the primary ray reaches the volume (`!(sky_sdf(entry) > MAX_RAY_DISTANCE)` after the
+// shader's own FindEntryExit march), 0 for a sky pixel.  Test aid: the CUDA tracker decides most sky pixels with a conservative
+// analytic test instead of running the march, and tests/test_oracle_tracker.py checks that test against this function.
+void hpmo_primary_hit(const HpmoScene* sc, const HpmoConfig* cfg, const HpmoCamera* cam, uint8_t* hit) {
+    const uint32_t W = cfg->width, H = cfg->height;
+    const float inv_w = 1.0f / (float)W, inv_h = 1.0f / (float)H;
+    const float* M = cam->inv_proj_view;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t yy = 0; yy < (int64_t)H; yy++) {
+        for (uint32_t x = 0; x < W; x++) {
+            Ctx c = make_ctx(sc);
+            const float u = (float)x * inv_w, v = (float)yy * inv_h;
+            const float sx = (u * 2.0f) - 1.0f, sy = (v * 2.0f) - 1.0f, sz = 0.0f, sw = 1.0f;
+            float wp[4];
+            for (int r = 0; r < 4; r++) wp[r] = ((M[0 + r] * sx + M[4 + r] * sy) + M[8 + r] * sz) + M[12 + r] * sw;
+            V3 pixel_world = {wp[0] / wp[3], wp[1] / wp[3], wp[2] / wp[3]};
+            V3 ro = {cam->pos[0], cam->pos[1], cam->pos[2]};
+            V3 rd = normalize3(pixel_world - ro);
+            V3 entry, exit;
+            c.find_entry_exit(ro, rd, &entry, &exit);
+            hit[(size_t)yy * W + x] = c.sky_sdf(entry) > MAX_RAY_DISTANCE ? 0 : 1;
+        }
+    }
+}
+
 // gen_rays.comp main + TracePath.  Outputs are the four RGBA32F images of the reference, kept as
 // planar-free AoS: primary_color[W*H][4] (rgb, factor), info[W*H] (didScatter as 0/1),
 // nrc_origin[W*H][3], nrc_dir[W*H][3]; pixel (x,y) lives at y*W + x.  Returns #density lookups.

@@ -210,3 +210,52 @@ def test_reference_exr_scenes_1_2_5_parameters(oracle_lib):
         both = (ref[..., 1] > 0.5) & (img[..., 3] > 0.5)
         alpha_err[density] = abs(img[..., 3][both].mean() - ref[..., 1][both].mean())
     assert alpha_err[0.8] <= 0.005 and alpha_err[1.6] >= 0.015, alpha_err
+
+
+def np_primary_ray_misses(ro, rd, half_sky):
+    """fp32 restatement of TrackerT::primary_ray_misses (csrc/hpm_kernels.cuh): the conservative analytic sky test of the CUDA tracker"""
+    f = np.float32
+    near = (np.abs(ro).sum(dtype=f) < f(1.0e4))
+    t_in = np.full(rd.shape[:-1], f(-3.0e38), f); t_out = np.full(rd.shape[:-1], f(3.0e38), f)
+    miss = np.zeros(rd.shape[:-1], bool)
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        for k in range(3):
+            h = f(half_sky[k]) + f(1.0)
+            d = rd[..., k]
+            live = np.abs(d) >= f(1.0e-6)
+            inv = (f(1.0) / d).astype(f)
+            t1 = ((-h - ro[k]) * inv).astype(f); t2 = ((h - ro[k]) * inv).astype(f)
+            t_in = np.where(live, np.maximum(t_in, np.minimum(t1, t2)), t_in)
+            t_out = np.where(live, np.minimum(t_out, np.maximum(t1, t2)), t_out)
+            miss |= (~live) & (abs(ro[k]) > h + f(1.0))
+    return near & (miss | (t_in > t_out) | (t_out < f(0.0)))
+
+
+@pytest.mark.parametrize("pose", [None, ((0.0, 0.0, -140.0), (0.0, 0.0, 1.0)), ((90.0, 40.0, -30.0), (-0.9, -0.3, 0.3)), ((0.0, 120.0, 5.0), (0.05, -1.0, 0.0)),
+                                  ((-64.0, 21.3, 0.0), (0.0, 0.0, 1.0)), ((40.0, 30.0, -50.0), (-0.2, -0.1, 1.0)), ((10.0, 5.0, 0.0), (1.0, 0.0, 0.2)),
+                                  ((64.0, 0.0, 0.0), (1.0, 0.0, 0.0))])
+def test_sky_cull_is_conservative(oracle_lib, pose):
+    """The CUDA tracker skips the FindEntryExit march of a primary ray when an analytic test says the ray cannot reach the volume.
+    Every pixel the test culls must be a sky pixel of the shader's own march (the oracle), for cameras outside, beside, above and
+    grazing the box; and the test must actually fire on most sky pixels (otherwise it is useless, not wrong)."""
+    from nrc_hpm_renderer_b200 import Camera
+    O = oracle_lib
+    osc, grid = small_scene(O)
+    Wd, Hd = 192, 108
+    cam = Camera(aspect=Wd / Hd) if pose is None else Camera(pos=pose[0], view_dir=pose[1], aspect=Wd / Hd)
+    cfg = O.make_config(Wd, Hd, 16, 8, 12, 12)
+    hit = O.primary_hit(osc, cfg, O.make_camera(cam.inv_proj_view, cam.pos))
+    f = np.float32
+    M = np.asarray(cam.inv_proj_view, f).reshape(-1)
+    xs = (np.arange(Wd, dtype=f) * (f(1.0) / f(Wd)))[None, :]; ys = (np.arange(Hd, dtype=f) * (f(1.0) / f(Hd)))[:, None]
+    sx = (xs * f(2.0) - f(1.0)) + np.zeros_like(ys); sy = (ys * f(2.0) - f(1.0)) + np.zeros_like(xs)
+    wp = [((M[0 + r] * sx + M[4 + r] * sy) + M[8 + r] * f(0.0)) + M[12 + r] * f(1.0) for r in range(4)]
+    ro = np.asarray(cam.pos, f)
+    d = np.stack([(wp[k] / wp[3]).astype(f) - ro[k] for k in range(3)], -1).astype(f)
+    rd = (d * (f(1.0) / np.sqrt((d * d).sum(-1, dtype=f)))[..., None]).astype(f)
+    half = np.array([osc.sky_size[0], osc.sky_size[1], osc.sky_size[2]], f) * f(0.5)
+    culled = np_primary_ray_misses(ro, rd, half)
+    assert not np.any(culled & (hit == 1)), "analytic sky test culled a pixel whose march reaches the volume"
+    sky = hit == 0
+    if sky.sum() > 100:
+        assert (culled & sky).sum() >= 0.9 * sky.sum()
