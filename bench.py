@@ -432,7 +432,8 @@ def run_ours(args):
         exchange_info = {"kind": "own kernel over NVLink peer memory (nrc_peer_adam_kernel): reduce-scatter of the gradient slice, Adam on the slice, all-gather of the fp16 weights, pipelined span by span" if peer else "NCCL all-reduce",
                          "bytes_per_training_step": exchange.bytes_per_step, "exchanges_per_step": TRAIN_BATCHES,
                          "ms_per_step_single_gpu_schedule_without_exchange": ms_solo, "exposed_ms_per_step": ms_step - ms_solo,
-                         "schedule": "nrc_infer_and_train: Inference() then Train(), each training step = forward/backward kernel + one peer kernel" if peer else "serial", "check": check}
+                         "schedule": "nrc_infer_and_train: each training step = forward/backward kernel + one peer kernel (reduce-scatter + Adam + weight all-gather); "
+                                     "inference chunks overlap the peer kernels unless NRCHPM_OVERLAP=0" if peer else "serial", "check": check}
 
     # ---- e2e: host buffers through the C ABI (pinned memory), H2D + D2H every step
     pin_in = [torch.from_numpy(synth_records(rng, N_INFER)).pin_memory() for _ in range(2)]
@@ -488,7 +489,9 @@ def run_ours(args):
         achieved_gbs = BYTES_PER_QUERY * N_INFER / (ms_kernel * 1e-3) / 1e9
         achieved_tf = FLOP_PER_QUERY_H6 * N_INFER / (ms_kernel * 1e-3) / 1e12
         cfg = base_config(world)
-        schedule = "Inference() then Train(), serial (reference order)"
+        overlapped = world > 1 and peer and os.environ.get("NRCHPM_OVERLAP", "1") != "0"
+        schedule = ("nrc_infer_and_train (C++): the frame's inference, cut into one chunk per training step, runs underneath the gradient exchanges from a snapshot "
+                    "of the pre-training EMA weights (same results as the reference order)") if overlapped else "Inference() then Train(), serial (reference order)"
         roof = {"kernel": "nrc_infer_ws_kernel<48,4,1,4> (hash-grid/OneBlob encode in 4 producer warpgroups -> smem ring -> 7-layer tcgen05 MLP in 1 consumer warpgroup + fp32 output)",
                 "bound": "hbm", "achieved": achieved_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / pk["hbm_gbs"],
                 "traffic": (ex or {}).get("dram_bytes_per_launch"), "traffic_source": (ex or {}).get("file"),

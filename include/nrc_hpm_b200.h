@@ -44,7 +44,8 @@ typedef struct nrc_cache nrc_cache;
  * config_json is the tiny-cuda-nn model JSON the reference builds there: {"loss":{"otype":"RelativeL2Luminance"},
  * "optimizer":{"otype":"EMA","decay":d,"nested":{"otype":"Adam","learning_rate":lr}},
  * "encoding":{"otype":"Composite","nested":[pos,dir]}, "network":{"otype":"FullyFusedMLP","activation":"ReLU",
- * "output_activation":"None","n_neurons":64,"n_hidden_layers":H}} plus the three AppConfig batch fields as
+ * "output_activation":"None","n_neurons":W,"n_hidden_layers":H}} -- W = 64 or 128 (AppConfig nnWidth, src/AppConfig.cpp:169;
+ * the 128-neuron network takes at most 6 hidden layers: its weights stay resident in shared memory) -- plus the three AppConfig batch fields as
  * optional top-level keys "infer_batch_size", "train_batch_size", "train_batch_count" (defaults 2^21, 2^14, 4)
  * and "compat":{"oneblob_soa_bug":true|false} (default true = bug-for-bug tcnn behaviour).
  * seed: tcnn Trainer seed (1337 in the reference, trainer.h:50-57). */

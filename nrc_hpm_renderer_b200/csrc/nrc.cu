@@ -4,6 +4,7 @@
 // (trainer.h:50-87 initialisation, :163-211 training_step / loss; network_with_input_encoding.h:115-130 parameter order).
 #include "nrc_host.h"
 #include "nrc_kernels.cuh"
+#include "nrc_wide_kernels.cuh"
 #include "mini_json.h"
 
 #include <algorithm>
@@ -117,7 +118,7 @@ static uint32_t grid_resolution(float scale) { return (uint32_t)ceilf(scale) + 1
 
 void NrcCache::derive() {
     const NrcConfig& c = cfg_;
-    NRCHPM_REQUIRE(c.n_neurons == 64, "n_neurons must be 64 (tcgen05 tile of this build)");
+    NRCHPM_REQUIRE(c.n_neurons == 64 || c.n_neurons == 128, "n_neurons must be 64 or 128 (the widths tiny-cuda-nn's FullyFusedMLP is used with by the reference, src/AppConfig.cpp:169)");
     NRCHPM_REQUIRE(c.n_hidden_layers >= 1 && c.n_hidden_layers <= 8, "n_hidden_layers must be in [1, 8]");
     NRCHPM_REQUIRE(c.n_features == 2, "HashGrid n_features_per_level must be 2");
     NRCHPM_REQUIRE(c.n_levels >= 1 && c.n_levels <= kMaxLevels, "HashGrid n_levels must be in [1, 16]");
@@ -353,6 +354,17 @@ void NrcCache::get_params(int which, float* out) {
 
 void NrcCache::setup_kernels() {
     const int H = cfg_.n_hidden_layers;
+    if (wide()) {
+        // 128 neurons (nrc_wide_kernels.cuh): the resident weight image bounds the depth; two tiles per CTA if their input tiles still fit
+        NRC_DISPATCH_INW(enc_.in_w, {
+            NRCHPM_REQUIRE(wide_fwd_smem_bytes<IN_W>(H, 1) <= 227 * 1024, "128-neuron network: at most 6 hidden layers fit the shared-memory weight image");
+            wide_wgs_ = wide_fwd_smem_bytes<IN_W>(H, 2) <= 227 * 1024 ? 2 : 1;
+            NRCHPM_CUDA(cudaFuncSetAttribute(nrc_wide_forward_kernel<IN_W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_fwd_smem_bytes<IN_W>(H, wide_wgs_)));
+            NRCHPM_CUDA(cudaFuncSetAttribute(nrc_wide_forward_kernel<IN_W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_fwd_smem_bytes<IN_W>(H, wide_wgs_)));
+            NRCHPM_CUDA(cudaFuncSetAttribute(nrc_wide_backward_kernel<IN_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_bwd_smem_bytes<IN_W>(H)));
+            NRCHPM_CUDA(cudaFuncSetAttribute(nrc_wide_dw_kernel<IN_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideDwSmemBytes));
+        });
+    }
     NRC_DISPATCH_INW(enc_.in_w, {
         NRCHPM_CUDA(cudaFuncSetAttribute(nrc_forward_kernel<IN_W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fwd_smem_bytes<IN_W>(H, kInferWgs) + infer_smem_level_bytes())));
         NRCHPM_CUDA(cudaFuncSetAttribute(nrc_forward_kernel<IN_W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem_bytes<IN_W>(H)));
@@ -394,7 +406,7 @@ bool NrcCache::fused_training_fits() const {
     const int H = cfg_.n_hidden_layers;
     size_t smem = 0;
     NRC_DISPATCH_INW(enc_.in_w, { smem = train_smem_bytes<IN_W>(H); });
-    return train_tmem_cols(enc_.in_w, H) <= 512 && smem <= 227 * 1024;
+    return !wide() && train_tmem_cols(enc_.in_w, H) <= 512 && smem <= 227 * 1024;
 }
 
 // bytes of the coarse hash-grid levels the inference kernel stages in shared memory (0: none)
@@ -442,6 +454,15 @@ void NrcCache::inference_with(const __half* params, const float* d_in, float* d_
     a.tl = timeline_slot();
     const uint32_t tiles = (n + kTile - 1) / kTile;
     uint32_t grid, threads;
+    if (wide()) {
+        // 128 neurons: persistent grid, one CTA per SM (176 KB weight image), `wide_wgs_` tiles in flight per CTA
+        const uint32_t wgs = tiles >= (uint32_t)sm_count_ * 2 ? (uint32_t)wide_wgs_ : 1u;
+        grid = std::min<uint32_t>((tiles + wgs - 1) / wgs, (uint32_t)sm_count_);
+        if (max_ctas) grid = std::min(grid, max_ctas);
+        NRC_DISPATCH_INW(enc_.in_w, { launch_hot(nrc_wide_forward_kernel<IN_W, false>, grid, wgs * 128, wide_fwd_smem_bytes<IN_W>(cfg_.n_hidden_layers, (int)wgs), s, a); });
+        check_launch("nrc_wide_forward_kernel<infer>");
+        return;
+    }
     if (infer_groups_ > 0) {
         const uint32_t g = (uint32_t)infer_groups_;
         grid = std::min<uint32_t>((tiles + g - 1) / g, (uint32_t)sm_count_);
@@ -485,8 +506,8 @@ void NrcCache::ensure_train_scratch(uint32_t B) {
     const int H = cfg_.n_hidden_layers;
     if (!(train_fused_ && fused_training_fits())) {       // the fused kernel keeps these in shared / tensor memory
         x16_.allocate((size_t)B * enc_.in_w);
-        acts_.allocate((size_t)H * B * kWidth);
-        dacts_.allocate((size_t)H * B * kWidth);
+        acts_.allocate((size_t)H * B * cfg_.n_neurons);
+        dacts_.allocate((size_t)H * B * cfg_.n_neurons);
         dx16_.allocate((size_t)B * enc_.in_w);
     }
     out16_.allocate((size_t)B * kOutPad);
@@ -538,6 +559,39 @@ void NrcCache::training_step_three_kernels(const float* d_in, const float* d_tar
     const uint32_t tiles = B / kTile;
     uint32_t grid, threads;
     launch_shape(tiles, grid, threads);
+    if (wide()) {
+        // 128 neurons: one CTA per SM; small batches spread one tile per CTA over the SMs, large ones keep two tiles in flight per CTA
+        const uint32_t wgs = tiles >= (uint32_t)sm_count_ * 2 ? (uint32_t)wide_wgs_ : 1u;
+        const uint32_t wgrid = std::min<uint32_t>((tiles + wgs - 1) / wgs, (uint32_t)sm_count_);
+        FwdArgs f{};
+        f.enc = enc_; f.params = w16_.ptr; f.n_mlp = (uint32_t)n_mlp_; f.n_hidden = H;
+        f.in = d_in; f.n = B; f.target = d_target;
+        f.x16 = x16_.ptr; f.acts = acts_.ptr; f.out16 = out16_.ptr; f.dout16 = dout16_.ptr; f.loss_partials = loss_partials_.ptr;
+        f.loss_scale = cfg_.loss_scale;
+        NRC_DISPATCH_INW(enc_.in_w, { launch_hot(nrc_wide_forward_kernel<IN_W, true>, wgrid, wgs * 128, wide_fwd_smem_bytes<IN_W>(H, (int)wgs), s, f); });
+        check_launch("nrc_wide_forward_kernel<train>");
+        BwdArgs b{};
+        b.enc = enc_; b.params = w16_.ptr; b.n_mlp = (uint32_t)n_mlp_; b.n_hidden = H; b.n = B;
+        b.in = d_in; b.acts = acts_.ptr; b.dout16 = dout16_.ptr; b.dacts = dacts_.ptr;
+        b.need_dx = n_grid_ ? 1 : 0;
+        b.dx16 = (n_grid_ && keep_dx_) ? dx16_.ptr : nullptr;
+        b.grid_grad = n_grid_ ? grad16_.ptr + n_mlp_ : nullptr;
+        b.loss_partials = loss_partials_.ptr; b.loss_out = loss_dev_.ptr; b.n_loss_partials = tiles;
+        NRC_DISPATCH_INW(enc_.in_w, { launch_hot(nrc_wide_backward_kernel<IN_W>, wgrid, wgs * 128, wide_bwd_smem_bytes<IN_W>(H), s, b); });
+        check_launch("nrc_wide_backward_kernel");
+        grid_grad_dirty_ = n_grid_ != 0;
+        DwArgs d{};
+        d.n_hidden = H; d.n = B; d.n_mlp = (uint32_t)n_mlp_;
+        // chunks x (H + 1) CTAs, one per SM (128 KB of operand stages): ~3 waves at the reference's 2^14 batch
+        const uint32_t want_chunks = tiles <= 1024 ? std::min<uint32_t>(tiles, 64u) : std::min<uint32_t>(kMaxDwChunks, tiles / 16);
+        const uint32_t tiles_per_chunk = (tiles + want_chunks - 1) / want_chunks;
+        d.kc = tiles_per_chunk * kTile;
+        dw_chunks_ = (B + d.kc - 1) / d.kc;
+        d.x16 = x16_.ptr; d.acts = acts_.ptr; d.dacts = dacts_.ptr; d.dout16 = dout16_.ptr; d.partials = dw_partials_.ptr;
+        NRC_DISPATCH_INW(enc_.in_w, { nrc_wide_dw_kernel<IN_W><<<dim3(dw_chunks_, H + 1), 128, kWideDwSmemBytes, s>>>(d); });
+        check_launch("nrc_wide_dw_kernel");
+        return;
+    }
     {
         FwdArgs a{};
         a.enc = enc_; a.params = w16_.ptr; a.n_mlp = (uint32_t)n_mlp_; a.n_hidden = H;

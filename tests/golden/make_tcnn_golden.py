@@ -20,12 +20,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 BIN = os.path.join(ROOT, "oracle", "_ref", "tcnn_oracle")
 SKY_HALF = np.array([62.317, 42.295, 76.707], dtype=np.float32) / 2  # skySize/2
 
-CONFIGS = [  # name, pos, dir, depth, n_infer, batch, steps
-    ("hash_ob_d6", 0, 0, 6, 1024, 256, 16),
-    ("tri_ob_d5", 2, 0, 5, 1024, 256, 16),
-    ("hash_tri_d3", 0, 2, 3, 512, 256, 4),
-    ("id_id_d2", 1, 1, 2, 512, 256, 4),
-    ("freq_ob_d4", 3, 0, 4, 512, 256, 4),
+CONFIGS = [  # name, pos, dir, depth, n_infer, batch, steps, n_neurons
+    ("hash_ob_d6", 0, 0, 6, 1024, 256, 16, 64),
+    ("tri_ob_d5", 2, 0, 5, 1024, 256, 16, 64),
+    ("hash_tri_d3", 0, 2, 3, 512, 256, 4, 64),
+    ("id_id_d2", 1, 1, 2, 512, 256, 4, 64),
+    ("freq_ob_d4", 3, 0, 4, 512, 256, 4, 64),
+    # nnWidth = 128 (reference src/AppConfig.cpp:169; tcnn instantiates FullyFusedMLP<__half, 128>, src/network.cu:117-118)
+    ("hash_ob_d6_w128", 0, 0, 6, 1024, 256, 16, 128),
+    ("tri_ob_d5_w128", 2, 0, 5, 1024, 256, 16, 128),
 ]
 
 
@@ -43,7 +46,7 @@ def main():
     out_root = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out_root, exist_ok=True)
     only = set(sys.argv[1:])
-    for name, pos, dr, depth, n_infer, batch, steps in CONFIGS:
+    for name, pos, dr, depth, n_infer, batch, steps, width in CONFIGS:
         if only and name not in only:
             continue
         rng = np.random.default_rng(1337 + pos * 10 + dr)
@@ -53,7 +56,7 @@ def main():
         train_in = make_records(rng, steps * batch)
         train_tgt = (rng.random((steps * batch, 3), dtype=np.float32) * 2).astype(np.float32)
         infer_in.tofile(work + "/infer_in.f32"); train_in.tofile(work + "/train_in.f32"); train_tgt.tofile(work + "/train_tgt.f32")
-        cmd = [BIN, "dump", f"out={work}", f"pos={pos}", f"dir={dr}", f"depth={depth}", f"n_infer={n_infer}", f"batch={batch}",
+        cmd = [BIN, "dump", f"out={work}", f"pos={pos}", f"dir={dr}", f"depth={depth}", f"width={width}", f"n_infer={n_infer}", f"batch={batch}",
                f"steps={steps}", f"infer_in={work}/infer_in.f32", f"train_in={work}/train_in.f32", f"train_tgt={work}/train_tgt.f32"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         print(res.stdout, res.stderr, file=sys.stderr)
@@ -64,7 +67,7 @@ def main():
             if line.startswith("{"):
                 meta.update(json.loads(line))
         P, inw = meta["n_params"], meta["padded_input"]
-        n_mlp = 64 * inw + (depth - 1) * 64 * 64 + 16 * 64
+        n_mlp = width * inw + (depth - 1) * width * width + 16 * width
         f32 = lambda f: np.fromfile(f"{work}/{f}", dtype=np.float32)
         f16 = lambda f: np.fromfile(f"{work}/{f}", dtype=np.float16)
         grad0 = f16("grad_step0.f16")
@@ -77,7 +80,7 @@ def main():
         pick = lambda a: a[grid_idx]
         np.savez_compressed(
             os.path.join(out_root, f"tcnn_{name}.npz"),
-            pos=pos, dir=dr, depth=depth, n_infer=n_infer, batch=batch, steps=steps, n_params=P, n_mlp=n_mlp, padded_input=inw,
+            pos=pos, dir=dr, depth=depth, width=width, n_infer=n_infer, batch=batch, steps=steps, n_params=P, n_mlp=n_mlp, padded_input=inw,
             infer_in=infer_in, train_in=train_in, train_tgt=train_tgt,
             grid_idx=grid_idx,
             params_init_mlp=params_init[:n_mlp], params_init_grid=pick(params_init),

@@ -54,7 +54,8 @@ def check_gen_rays(r, ref, W, H, min_same=0.99, min_agree=0.97):
     return info, agree
 
 
-def test_config1_256x256_tracking_inference_training_vs_oracles(oracle_lib):
+@pytest.mark.parametrize("width", [64, 128])          # nnWidth of the reference's command line (src/AppConfig.cpp:169): both tcgen05 kernel families
+def test_config1_256x256_tracking_inference_training_vs_oracles(oracle_lib, width):
     from nrc_hpm_renderer_b200 import AppConfig, Camera, HpmSceneConfig
     from nrc_hpm_renderer_b200 import nrc as N, renderer as R
     O = oracle_lib
@@ -62,9 +63,10 @@ def test_config1_256x256_tracking_inference_training_vs_oracles(oracle_lib):
     grid = quarter_cloud()
     app = AppConfig.default()
     app.scene = HpmSceneConfig.preset(0)
+    app.nn_width = width
     app.train_batch_count = 1                                       # C1: one training step of 2^14 records (128 x 128 train pixels, XDist 2)
     cache = N.NeuralRadianceCache(app)
-    o = O.NrcOracle(O.nrc_config(app.pos_enc_id, app.dir_enc_id, app.nn_depth))
+    o = O.NrcOracle(O.nrc_config(app.pos_enc_id, app.dir_enc_id, app.nn_depth, width))
     assert np.array_equal(cache.get_params(N.MASTER), o.get(o.MASTER))
     # Inference() reads the EMA weights, which are zero before the first step (Q7): load the initial weights as EMA on both sides
     cache.set_ema(cache.get_params(N.MASTER)); o.set_ema(o.get(o.MASTER))

@@ -13,7 +13,8 @@ from conftest import golden
 
 pytestmark = pytest.mark.gpu
 
-CONFIGS = ["hash_ob_d6", "tri_ob_d5", "hash_tri_d3", "id_id_d2", "freq_ob_d4"]
+CONFIGS = ["hash_ob_d6", "tri_ob_d5", "hash_tri_d3", "id_id_d2", "freq_ob_d4",
+           "hash_ob_d6_w128", "tri_ob_d5_w128"]          # nnWidth = 128: the 128-neuron kernels (csrc/nrc_wide_kernels.cuh)
 
 
 def rel_err(a, b, floor=1.0):
@@ -51,6 +52,7 @@ def make_cache(z, **kw):
     from nrc_hpm_renderer_b200.nrc import NeuralRadianceCache
     app = AppConfig.default()
     app.pos_enc_id, app.dir_enc_id, app.nn_depth = int(z["pos"]), int(z["dir"]), int(z["depth"])
+    app.nn_width = int(z["width"]) if "width" in z else 64
     return NeuralRadianceCache(app, **kw)
 
 
@@ -108,13 +110,13 @@ def test_inference_vs_tcnn(name):
     # 99.9 % of tcnn's outputs bit for bit, the maximum is 1.2e-2 (hash_ob_d6) / 3.1e-2 (tri_ob_d5); in fp32 mode p99 is 8e-3 / 7.8e-2:
     # outputs two decades below the rms are differences of O(rms) terms rounded to fp16 (ulp 5e-4 relative) layer by layer.
     import oracle as O
-    o = O.NrcOracle(O.nrc_config(int(z["pos"]), int(z["dir"]), int(z["depth"]), accum_fp16=0))
+    o = O.NrcOracle(O.nrc_config(int(z["pos"]), int(z["dir"]), int(z["depth"]), int(z["width"]) if "width" in z else 64, accum_fp16=0))
     ref = z["infer_working_step0"]
     dist = contract_distribution(out.cpu().numpy(), ref)
     base = contract_distribution(o.inference(z["infer_in"], use_ema=False), ref)
     report_parity(name, "inference_vs_tcnn", dist, base)
     if name != "freq_ob_d4":          # Frequency: tcnn evaluates __sinf (frequency.h:74) on arguments up to 2^11 pi; covered by the rms-floored bound above
-        assert dist["p50"] <= 2.5e-3
+        assert dist["p50"] <= (3e-3 if "w128" in name else 2.5e-3)      # 128 neurons: twice as many fp16 products per accumulator
         assert dist["p99"] <= max(1e-2, 1.5 * base["p99"]), (dist, base)
         assert dist["frac_gt_1e-2"] <= base["frac_gt_1e-2"] + 0.02, (dist, base)
 
@@ -170,25 +172,38 @@ def test_training_vs_tcnn(name):
     losses = np.array(losses); ref = z["losses"]
     assert np.all(np.isfinite(losses))
     assert abs(losses[0] - ref[0]) / ref[0] <= 1e-3
-    # later steps see slightly different weights (fp16 vs fp32 accumulation, atomic order): curve must track
-    assert np.max(np.abs(losses - ref) / np.maximum(ref, 1e-3)) <= 0.08, (losses, ref)
+    # later steps see slightly different weights (fp16 vs fp32 accumulation, atomic order): curve must track.  The 128-neuron
+    # fixtures contain a loss SPIKE (lr 0.01 on random targets: x2.3 at step 7 / x13 at step 12 in tcnn's own curve); from there on
+    # the trajectory is chaotic in the arithmetic -- the CPU oracle reproduces tcnn's curve to 0.3 % in fp16-accumulation mode and
+    # leaves it by 12 % at the spike in fp32 mode (tests/test_oracle_nrc.py) -- so the bound against tcnn holds up to the spike and
+    # the rest of the curve is held against the oracle with the CUDA path's own arithmetic (fp32 accumulation).
+    spike = next((i for i in range(2, len(ref)) if ref[i] > 1.5 * ref[i - 1]), len(ref))
+    assert np.max(np.abs(losses - ref)[:spike] / np.maximum(ref, 1e-3)[:spike]) <= 0.08, (losses, ref)
     out = torch.zeros((int(z["n_infer"]), 3), dtype=torch.float32, device="cuda")
     c.inference(dev(z["infer_in"]), out, int(z["n_infer"]), use_ema=True)
     torch.cuda.synchronize()
-    ref_out = z["infer_ema_final"]
+    if spike == len(ref):
+        ref_out = z["infer_ema_final"]
+    else:
+        import oracle as O
+        o = O.NrcOracle(O.nrc_config(int(z["pos"]), int(z["dir"]), int(z["depth"]), int(z["width"]) if "width" in z else 64, accum_fp16=0))
+        lo = np.array([o.training_step(z["train_in"][s * B:(s + 1) * B], z["train_tgt"][s * B:(s + 1) * B]) for s in range(steps)])
+        assert np.max(np.abs(losses - lo) / np.maximum(lo, 1e-3)) <= 0.15, (losses, lo)
+        ref_out = o.inference(z["infer_in"], use_ema=True)
     err = np.abs(out.cpu().numpy() - ref_out)
     assert np.nanmax(err) <= 0.05 * max(1.0, np.sqrt(np.nanmean(ref_out ** 2)))
 
 
-@pytest.mark.parametrize("pos,dr,depth", [(0, 0, 5), (2, 0, 6), (3, 0, 4), (1, 2, 1), (0, 1, 8), (3, 2, 8)])
-def test_against_oracle(pos, dr, depth, oracle_lib):
+@pytest.mark.parametrize("pos,dr,depth,width", [(0, 0, 5, 64), (2, 0, 6, 64), (3, 0, 4, 64), (1, 2, 1, 64), (0, 1, 8, 64), (3, 2, 8, 64),
+                                                 (0, 0, 6, 128), (2, 0, 5, 128), (1, 1, 1, 128), (0, 2, 3, 128)])
+def test_against_oracle(pos, dr, depth, width, oracle_lib):
     """same seeded inputs through the CUDA path and the CPU oracle: inference, one training step, gradients"""
     import torch
     from nrc_hpm_renderer_b200 import AppConfig, nrc as N
     O = oracle_lib
-    app = AppConfig.default(); app.pos_enc_id, app.dir_enc_id, app.nn_depth = pos, dr, depth
+    app = AppConfig.default(); app.pos_enc_id, app.dir_enc_id, app.nn_depth, app.nn_width = pos, dr, depth, width
     c = N.NeuralRadianceCache(app)
-    o = O.NrcOracle(O.nrc_config(pos, dr, depth))
+    o = O.NrcOracle(O.nrc_config(pos, dr, depth, width))
     assert c.n_params == o.n_params
     assert np.array_equal(c.get_params(N.MASTER), o.get(o.MASTER))
     rng = np.random.default_rng(5 + pos * 7 + dr)
