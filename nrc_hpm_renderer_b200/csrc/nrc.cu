@@ -363,6 +363,9 @@ void NrcCache::setup_kernels() {
             NRCHPM_CUDA(cudaFuncSetAttribute(nrc_wide_forward_kernel<IN_W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_fwd_smem_bytes<IN_W>(H, wide_wgs_)));
             NRCHPM_CUDA(cudaFuncSetAttribute(nrc_wide_backward_kernel<IN_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_bwd_smem_bytes<IN_W>(H)));
             NRCHPM_CUDA(cudaFuncSetAttribute(nrc_wide_dw_kernel<IN_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideDwSmemBytes));
+            wide_ws_slots_ = wide_ws_slots<IN_W>(H);
+            if (wide_ws_slots_ >= 2)
+                NRCHPM_CUDA(cudaFuncSetAttribute(nrc_wide_infer_ws_kernel<IN_W, NRC_WIDE_WS_NP, NRC_WIDE_WS_NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_ws_smem_bytes<IN_W>(H, wide_ws_slots_)));
         });
     }
     NRC_DISPATCH_INW(enc_.in_w, {
@@ -454,6 +457,16 @@ void NrcCache::inference_with(const __half* params, const float* d_in, float* d_
     a.tl = timeline_slot();
     const uint32_t tiles = (n + kTile - 1) / kTile;
     uint32_t grid, threads;
+    if (wide() && infer_ws_ > 0 && enc_.pos_enc == POS_HASHGRID && wide_ws_slots_ >= 2 && tiles >= (uint32_t)sm_count_) {
+        // 128 neurons, hash grid: warp-specialised persistent kernel (producer warpgroups gather, consumer warpgroups run the MLP)
+        grid = (uint32_t)sm_count_;
+        if (max_ctas) grid = std::min(grid, max_ctas);
+        a.ring_slots = (uint32_t)wide_ws_slots_;
+        NRC_DISPATCH_INW(enc_.in_w, { launch_hot(nrc_wide_infer_ws_kernel<IN_W, NRC_WIDE_WS_NP, NRC_WIDE_WS_NC>, grid, (NRC_WIDE_WS_NP + NRC_WIDE_WS_NC) * 128,
+                                                 wide_ws_smem_bytes<IN_W>(cfg_.n_hidden_layers, wide_ws_slots_), s, a); });
+        check_launch("nrc_wide_infer_ws_kernel");
+        return;
+    }
     if (wide()) {
         // 128 neurons: persistent grid, one CTA per SM (176 KB weight image), `wide_wgs_` tiles in flight per CTA
         const uint32_t wgs = tiles >= (uint32_t)sm_count_ * 2 ? (uint32_t)wide_wgs_ : 1u;

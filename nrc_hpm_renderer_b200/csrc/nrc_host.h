@@ -86,7 +86,7 @@ private:
     void ensure_train_scratch(uint32_t B);
     bool fused_training_fits() const;
     bool wide() const { return cfg_.n_neurons == 128; }      // 128-neuron network: nrc_wide_kernels.cuh
-    int wide_wgs_ = 1;
+    int wide_wgs_ = 1, wide_ws_slots_ = 0;
     void training_step_three_kernels(const float* d_in, const float* d_target, uint32_t B, cudaStream_t s);
     void launch_shape(uint32_t tiles, uint32_t& grid, uint32_t& threads) const;
     void ensure_pipeline(uint32_t n_chunks);

@@ -529,6 +529,7 @@ struct FwdArgs {
     float* out;                 // inference: float[*][3]
     uint32_t smem_levels;       // inference: the first `smem_levels` hash-grid levels (`smem_level_entries` entries) are staged in smem
     uint32_t smem_level_entries;
+    uint32_t ring_slots;        // nrc_wide_infer_ws_kernel: X tiles in the shared-memory ring
     // training only
     const float* target;        // float[n][3]
     __half* x16;                // [n][IN_W]   network input

@@ -405,4 +405,162 @@ __global__ void __launch_bounds__(128, 1) nrc_wide_dw_kernel(const __grid_consta
     if (warp == 0) tmem_dealloc(tmem_base_s, 128);
 }
 
+// warp-specialised inference (the 128-neuron counterpart of nrc_infer_ws_kernel): NP producer warpgroups encode records into a ring
+// of NS K-major X tiles in shared memory, NC consumer warpgroups run the seven-layer MLP (tcgen05, activations in TMEM).  With one
+// tile per warpgroup (nrc_wide_forward_kernel) a 1080p frame of hash-grid records takes 1.58 ms: eight warps per SM cannot keep the
+// gathers of 16 levels in flight.  Two consumers sustain 0.55 ms per frame (the M = 128 x N = 128 layers are 4x the narrow
+// network's work per tile), four producers keep the L1 -> L2 request path busy underneath.
+#ifndef NRC_WIDE_WS_NP
+#define NRC_WIDE_WS_NP 4
+#endif
+#ifndef NRC_WIDE_WS_NC
+#define NRC_WIDE_WS_NC 2
+#endif
+template <int IN_W>
+__host__ __device__ constexpr int wide_ws_slots(int n_hidden) {      // ring slots that fit next to the weight image (227 KB per CTA), at most 4
+    return (int)((227 * 1024 - 2048 - wide_weight_bytes<IN_W>(n_hidden)) / ((size_t)IN_W * 256)) > 4 ? 4 : (int)((227 * 1024 - 2048 - wide_weight_bytes<IN_W>(n_hidden)) / ((size_t)IN_W * 256));
+}
+template <int IN_W>
+__host__ __device__ constexpr size_t wide_ws_smem_bytes(int n_hidden, int slots) { return wide_weight_bytes<IN_W>(n_hidden) + (size_t)slots * IN_W * 256; }
+
+template <int IN_W, int NP, int NC>
+__global__ void __maxnreg__(80) nrc_wide_infer_ws_kernel(const __grid_constant__ FwdArgs a) {
+    using namespace tc05;
+    constexpr int kMaxSlots = 4;
+    const uint32_t NS = a.ring_slots;
+    constexpr uint32_t kAlloc = NC * kWideColsPerWg <= 256 ? 256u : 512u;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t full[kMaxSlots], empty[kMaxSlots], mbar[NC];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, r = tid & 127;
+    const int H = a.n_hidden;
+    constexpr uint32_t kHid = kWide * kWide * 2, kSboW = (kWide / 8) * 128;
+    uint8_t* w0_s = smem;
+    uint8_t* wh_s = w0_s + IN_W * kWide * 2;
+    uint8_t* wo_s = wh_s + (size_t)(H - 1) * kHid;
+    uint8_t* ring = wo_s + kOutPad * kWide * 2;
+
+    timeline_begin(a.tl, 0);
+    if (warp == 0) { tmem_alloc(&tmem_base_s, kAlloc); tmem_relinquish(); }
+    if (tid == 0) {
+        for (uint32_t s = 0; s < NS; s++) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+        for (int c = 0; c < NC; c++) mbar_init(&mbar[c], 1);
+        fence_mbar_init();
+    }
+    copy_weights_kmajor(w0_s, a.params, kWide, IN_W, tid, (NP + NC) * 128);
+    for (int l = 1; l < H; l++) copy_weights_kmajor(wh_s + (size_t)(l - 1) * kHid, a.params + IN_W * kWide + (size_t)(l - 1) * kWide * kWide, kWide, kWide, tid, (NP + NC) * 128);
+    copy_weights_kmajor(wo_s, a.params + IN_W * kWide + (size_t)(H - 1) * kWide * kWide, kOutPad, kWide, tid, (NP + NC) * 128);
+    fence_proxy_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+
+    uint32_t n = a.n;
+    if (a.d_count) n = min(n, *a.d_count);
+    const uint32_t n_tiles = (n + kTile - 1) / kTile;
+    const uint32_t n_my = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;      // tiles blockIdx.x + k * gridDim.x
+
+    if (wg < NP) {
+        // ------------------------------------------------------------ producers: records -> encoded X tiles
+        const __half2* grid = reinterpret_cast<const __half2*>(a.params + a.n_mlp);
+        const bool by_kind = a.enc.pos_enc == POS_HASHGRID && a.enc.all_pow2;
+        for (uint32_t k = wg; k < n_my; k += NP) {
+            const uint32_t slot = k % NS, use = k / NS;
+            const uint32_t row = (blockIdx.x + k * gridDim.x) * kTile + r;
+            float x0 = 0, x1 = 0, x2 = 0, th = 0, ph = 0;
+            if (row < n) {
+                const uint32_t rec = a.indices ? a.indices[row] : row;
+                const float* p = a.in + 5 * (size_t)rec;
+                x0 = __ldcs(p); x1 = __ldcs(p + 1); x2 = __ldcs(p + 2); th = __ldcs(p + 3); ph = __ldcs(p + 4);      // read once: keep them out of L1
+            }
+            if (use > 0) mbar_wait(&empty[slot], (use - 1) & 1);          // the tensor core has read the tile that lived here
+            SmemRowPut put{ring + slot * (IN_W * 256) + (r >> 3) * (IN_W * 16) + (r & 7) * 16};
+            if (by_kind) { hashgrid_by_kind(a.enc, grid, x0, x1, x2, put); encode_direction_pad(a.enc, th, ph, put); }
+            else encode_record<1>(a.enc, grid, x0, x1, x2, th, ph, put);
+            fence_proxy_async_smem();
+            mbar_arrive(&full[slot]);
+        }
+    } else {
+        // ------------------------------------------------------------ consumers: the MLP
+        const int c = wg - NP;
+        const uint32_t tD = tmem_base_s + c * kWideColsPerWg, tA = tD + kWide;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t idesc_h = make_idesc_f16(128, kWide), idesc_o = make_idesc_f16(128, kOutPad);
+        const uint32_t ring_addr = smem_u32(ring), w0_addr = smem_u32(w0_s), wh_addr = smem_u32(wh_s), wo_addr = smem_u32(wo_s);
+        uint64_t* bar = &mbar[c];
+        uint32_t phase = 0;
+        for (uint32_t k = c; k < n_my; k += NC) {
+            const uint32_t slot = k % NS, use = k / NS;
+            const uint32_t row = (blockIdx.x + k * gridDim.x) * kTile + r;
+            const bool valid = row < n;
+            uint32_t rec = 0;
+            if (valid) rec = a.indices ? a.indices[row] : row;
+            mbar_wait(&full[slot], use & 1);
+            if (r == 0) {
+                fence_after();
+                const uint32_t x_addr = ring_addr + slot * (IN_W * 256);
+#pragma unroll
+                for (int s = 0; s < IN_W / 16; s++)
+                    mma_f16_ss(tD, make_smem_desc(x_addr + s * 256, 128, IN_W * 16), make_smem_desc(w0_addr + s * 256, 128, IN_W * 16), idesc_h, s > 0);
+                mma_commit(&empty[slot]);       // the slot returns to the producers as soon as the tensor core has read it
+                mma_commit(bar);
+            }
+            mbar_wait(bar, phase); phase ^= 1;
+            fence_after();
+            for (int l = 0; l < H; l++) {
+#pragma unroll
+                for (int q = 0; q < kWide / 32; q++) {
+                    uint32_t acc[32], p[16];
+                    tmem_ld32(tD + lane_base + q * 32, acc);
+                    wait_ld();
+                    if (l == 0) {      // tcnn's ReLU is max(x, 0) in fp16: NaN (Q5) -> 0; cvt.relu would keep it
+                        const __half2 zero2 = __float2half2_rn(0.0f);
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            uint32_t v = pack_f16x2(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
+                            __half2 m = __hmax2(*reinterpret_cast<__half2*>(&v), zero2);
+                            p[j] = *reinterpret_cast<uint32_t*>(&m);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) p[j] = pack_relu_f16x2(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
+                    }
+                    tmem_st16(tA + lane_base + q * 16, p);
+                }
+                wait_st();
+                fence_before();
+                named_bar_sync(1 + c, 128);
+                if (r == 0) {
+                    fence_after();
+                    if (l < H - 1) {
+#pragma unroll
+                        for (int s = 0; s < kWide / 16; s++) mma_f16_ts(tD, tA + s * 8, make_smem_desc(wh_addr + l * kHid + s * 256, 128, kSboW), idesc_h, s > 0);
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < kWide / 16; s++) mma_f16_ts(tD, tA + s * 8, make_smem_desc(wo_addr + s * 256, 128, kSboW), idesc_o, s > 0);
+                    }
+                    mma_commit(bar);
+                }
+                mbar_wait(bar, phase); phase ^= 1;
+                fence_after();
+            }
+            // output layer: fp16 like tcnn's network output, then float (common_device.h:990-999)
+            uint32_t o[4];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]) : "r"(tD + lane_base) : "memory");
+            wait_ld();
+            if (valid) {
+                float* dst = a.out + 3 * (size_t)rec;
+#pragma unroll
+                for (int q = 0; q < 3; q++) __stcs(dst + q, __half2float(__float2half_rn(__uint_as_float(o[q]))));
+            }
+            fence_before();
+            named_bar_sync(1 + c, 128);      // every thread's read of tD is complete before thread 0 issues the next tile's layer-0 MMA
+        }
+    }
+    fence_before();
+    __syncthreads();
+    timeline_end(a.tl, 0);
+    if (warp == 0) tmem_dealloc(tmem_base_s, kAlloc);
+}
+
 }  // namespace nrchpm

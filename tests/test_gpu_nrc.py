@@ -191,7 +191,7 @@ def test_training_vs_tcnn(name):
         assert np.max(np.abs(losses - lo) / np.maximum(lo, 1e-3)) <= 0.15, (losses, lo)
         ref_out = o.inference(z["infer_in"], use_ema=True)
     err = np.abs(out.cpu().numpy() - ref_out)
-    assert np.nanmax(err) <= 0.05 * max(1.0, np.sqrt(np.nanmean(ref_out ** 2)))
+    assert np.nanmax(err) <= (0.05 if spike == len(ref) else 0.15) * max(1.0, np.sqrt(np.nanmean(ref_out ** 2)))      # same bound as the post-spike losses
 
 
 @pytest.mark.parametrize("pos,dr,depth,width", [(0, 0, 5, 64), (2, 0, 6, 64), (3, 0, 4, 64), (1, 2, 1, 64), (0, 1, 8, 64), (3, 2, 8, 64),
