@@ -91,4 +91,5 @@ def test_nrc_frames_converge_towards_reference():
     assert np.isfinite(img[..., :3]).all()
     both = (ref[..., 1] > 0.5)
     rel_bias = (img[..., 0][both].mean() - ref[..., 0][both].mean()) / ref[..., 0][both].mean()
+    print(f"NRC frames after 428 frames of online training at 240x135: rBias {rel_bias:+.4f} against reference/0/0.exr")
     assert -0.25 <= rel_bias <= 0.10, rel_bias
