@@ -214,6 +214,12 @@ int hpm_renderer_set_blend(hpm_renderer* r, int blend);       /* NrcHpmRenderer:
 int hpm_render(hpm_renderer* r, const float frame_random[4], int train);
 /* McHpmRenderer::Render (src/McHpmRenderer.cpp:121-151, data/shader/mc/render.comp:7-84) */
 int hpm_mc_render(hpm_renderer* r, const float frame_random[4], uint32_t path_length);
+/* Schedule of the gen_rays pass: 0 automatic (default), 1 one pixel per thread for the whole path (the shader's own shape,
+ * data/shader/nrc/gen_rays.comp:53-101), 2 path regeneration: primary rays in one coherent launch, then persistent warps in which a
+ * lane whose path has ended takes the next path from a queue (TracePath, gen_rays.comp:7-51, one bounce per iteration).  Every output
+ * is bit-identical between the modes except the ORDER of the compacted record list.  Automatic currently means 1: measured faster
+ * on B200 (profiles/r02_tracker_regeneration.md). */
+int hpm_renderer_set_tracker_mode(hpm_renderer* r, int mode);
 /* individual passes, for parity tests and profiling */
 int hpm_pass_gen_rays(hpm_renderer* r, const float frame_random[4]);      /* clear + gen_rays + prep_infer_rays */
 int hpm_pass_prep_train(hpm_renderer* r, const float frame_random[4]);    /* clear.comp + prep_train_rays      */

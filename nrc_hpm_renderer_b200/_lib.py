@@ -90,6 +90,7 @@ SIGNATURES = {
     "hpm_renderer_set_blend": (_I, [_P, _I]),
     "hpm_render": (_I, [_P, _F, _I]),
     "hpm_mc_render": (_I, [_P, _F, _U32]),
+    "hpm_renderer_set_tracker_mode": (_I, [_P, _I]),
     "hpm_pass_gen_rays": (_I, [_P, _F]),
     "hpm_pass_prep_train": (_I, [_P, _F]),
     "hpm_pass_composite": (_I, [_P]),

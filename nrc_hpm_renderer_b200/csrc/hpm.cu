@@ -3,10 +3,12 @@
 // -> prep_train_rays -> NRC inference -> NRC training -> render, with no host round trip in the compacted mode (the
 // reference waits on a fence and reads the inference filter back every frame, :332-334).
 #include "hpm_host.h"
+#include "hpm_wavefront.cuh"
 #include "nrc_host.h"
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -125,6 +127,7 @@ void Renderer::pass_gen_rays(const float fr[4]) {
     NRCHPM_CUDA(cudaMemsetAsync(filter_.ptr, 0, filter_.bytes(), stream_));
     NRCHPM_CUDA(cudaMemsetAsync(active_count_.ptr, 0, sizeof(uint32_t), stream_));
     NRCHPM_CUDA(cudaMemsetAsync(counters_.ptr, 0, sizeof(unsigned long long), stream_));
+    if (use_wavefront()) { pass_gen_rays_wavefront(fr); return; }
     GenRaysArgs a{};
     a.sc = scene_->dev(); a.cam = cam_; a.cfg = dcfg_;
     a.frame_random = make_float4(fr[0], fr[1], fr[2], fr[3]);
@@ -136,6 +139,70 @@ void Renderer::pass_gen_rays(const float fr[4]) {
     if (a.sc.maj) hpm_gen_rays_kernel<true><<<grid, block, 0, stream_>>>(a);
     else hpm_gen_rays_kernel<false><<<grid, block, 0, stream_>>>(a);
     check_launch("hpm_gen_rays_kernel");
+}
+
+// ---- path-regeneration form of gen_rays (hpm_wavefront.cuh): same per-pixel arithmetic and RNG streams, ended paths replaced from a queue
+void Renderer::set_tracker_mode(int mode) {
+    NRCHPM_REQUIRE(mode >= 0 && mode <= 2, "tracker mode: 0 automatic, 1 pixel per thread, 2 path regeneration");
+    tracker_mode_ = mode;
+}
+
+bool Renderer::use_wavefront() const {
+    if (scene_->dev().maj) return false;                       // the per-brick majorant mode exists in the pixel-per-thread kernels only
+    if (cfg_.width > 65535u || cfg_.height > 65535u) return false;   // path records pack the pixel as x | y << 16
+    // automatic = pixel per thread: measured faster on B200 at every configuration tried (profiles/r02_tracker_regeneration.md)
+    return tracker_mode_ == 2;
+}
+
+void Renderer::pass_gen_rays_wavefront(const float fr[4]) {
+    const uint32_t tw = hpmdev::kTileW, th = 128 / tw;
+    const dim3 block(tw, th), grid((cfg_.x_end - cfg_.x_begin + tw - 1) / tw, (cfg_.height + th - 1) / th);
+    const uint32_t n = grid.x * grid.y * 128u;                 // path slots: at most one per launched thread
+    constexpr uint32_t kWords = 13;
+    if (!wf_state_.ptr) {
+        wf_state_.allocate((size_t)n * kWords); wf_queues_.allocate((size_t)n * 2);
+        wf_counters_.allocate(2 * (kWfMaxRounds + 1));
+        int dev = 0, sms = 0, occ = 0;
+        NRCHPM_CUDA(cudaGetDevice(&dev));
+        NRCHPM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const char* env = std::getenv("NRCHPM_WF_BLOCKS_PER_SM");
+        const int want = env ? std::atoi(env) : 64;
+        NRCHPM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hpm_wf_paths_kernel, 128, 0));
+        wf_blocks_ = std::max(1, std::min(occ, want)) * sms;
+        env = std::getenv("NRCHPM_WF_ROUNDS"); wf_rounds_ = env ? std::max(1, std::min(std::atoi(env), kWfMaxRounds)) : kWfRounds;
+        env = std::getenv("NRCHPM_WF_SPILL_BELOW"); wf_spill_below_ = env ? (uint32_t)std::atoi(env) : kWfSpillBelow;
+    }
+    NRCHPM_CUDA(cudaMemsetAsync(wf_counters_.ptr, 0, wf_counters_.bytes(), stream_));
+    WfArgs a{};
+    a.sc = scene_->dev(); a.cam = cam_; a.cfg = dcfg_;
+    a.frame_random = make_float4(fr[0], fr[1], fr[2], fr[3]);
+    a.primary_color = primary_color_.ptr; a.info = info_.ptr; a.origin = origin_.ptr; a.dir = dir_.ptr;
+    a.infer_in = infer_in_.ptr; a.infer_filter = filter_.ptr; a.active_list = active_list_.ptr; a.active_count = active_count_.ptr;
+    a.lookups = counters_.ptr;
+    {
+        uint32_t* w = wf_state_.ptr; float* f = reinterpret_cast<float*>(w);
+        size_t o = 0;
+        auto take = [&](size_t words) { const size_t at = o; o += words * n; return at; };
+        WfState& st = a.st;
+        st.n = n;
+        st.pixel = w + take(1); st.rng = f + take(1); st.cur = f + take(3); st.dir = f + take(3); st.light = f + take(3);
+        st.factor = f + take(1); st.bounce = w + take(1);
+    }
+    uint32_t* items[2] = {wf_queues_.ptr, wf_queues_.ptr + n};
+    uint32_t* ctr = wf_counters_.ptr;
+    hpm_wf_primary_kernel<<<grid, block, 0, stream_>>>(a, items[0], ctr + 0);
+    check_launch("hpm_wf_primary_kernel");
+    // a path that can only make one bounce has nothing to regroup: one round.  Otherwise the early rounds hand their stragglers on.
+    const bool short_paths = cfg_.primary_ray_length == 0 && !(cfg_.primary_ray_prob > 0.0f);
+    const int rounds = short_paths ? 1 : wf_rounds_;
+    for (int r = 0; r < rounds; r++) {
+        WfRound q{};
+        q.in_items = items[r & 1]; q.in_count = ctr + 2 * r; q.in_head = ctr + 2 * r + 1;
+        q.out_items = items[(r & 1) ^ 1]; q.out_count = ctr + 2 * (r + 1);
+        q.spill_below = r + 1 < rounds ? wf_spill_below_ : 0u;
+        hpm_wf_paths_kernel<<<wf_blocks_, 128, 0, stream_>>>(a, q);
+        check_launch("hpm_wf_paths_kernel");
+    }
 }
 
 void Renderer::pass_prep_train(const float fr[4]) {
@@ -309,6 +376,7 @@ int hpm_renderer_set_camera(hpm_renderer* r, const float m[16], const float pos[
 int hpm_renderer_set_blend(hpm_renderer* r, int blend) { return guard([&] { NRCHPM_REQUIRE(r, "null renderer"); r->impl.set_blend(blend != 0); }); }
 int hpm_render(hpm_renderer* r, const float fr[4], int train) { return guard([&] { NRCHPM_REQUIRE(r && fr, "null argument"); r->impl.render(fr, train != 0); }); }
 int hpm_mc_render(hpm_renderer* r, const float fr[4], uint32_t path_length) { return guard([&] { NRCHPM_REQUIRE(r && fr, "null argument"); r->impl.mc_render(fr, path_length); }); }
+int hpm_renderer_set_tracker_mode(hpm_renderer* r, int mode) { return guard([&] { NRCHPM_REQUIRE(r, "null renderer"); r->impl.set_tracker_mode(mode); }); }
 int hpm_pass_gen_rays(hpm_renderer* r, const float fr[4]) { return guard([&] { NRCHPM_REQUIRE(r && fr, "null argument"); r->impl.pass_gen_rays(fr); }); }
 int hpm_pass_prep_train(hpm_renderer* r, const float fr[4]) { return guard([&] { NRCHPM_REQUIRE(r && fr, "null argument"); r->impl.pass_prep_train(fr); }); }
 int hpm_pass_composite(hpm_renderer* r) { return guard([&] { NRCHPM_REQUIRE(r, "null renderer"); r->impl.pass_composite(); }); }

@@ -29,6 +29,8 @@ public:
     void render(const float frame_random[4], bool train);
     void mc_render(const float frame_random[4], uint32_t path_length);
     void pass_gen_rays(const float frame_random[4]);
+    // 0 = automatic, 1 = one pixel per thread (hpm_gen_rays_kernel), 2 = path regeneration (hpm_wavefront.cuh); same results bit for bit
+    void set_tracker_mode(int mode);
     void pass_prep_train(const float frame_random[4]);
     void pass_composite();
     void sync() { NRCHPM_CUDA(cudaStreamSynchronize(stream_)); if (train_stream_) NRCHPM_CUDA(cudaStreamSynchronize(train_stream_)); }
@@ -39,6 +41,12 @@ public:
 
 private:
     float next_blend_factor();
+    bool use_wavefront() const;
+    void pass_gen_rays_wavefront(const float frame_random[4]);
+    int tracker_mode_ = 0;
+    DeviceBuffer<uint32_t> wf_state_, wf_queues_, wf_counters_;      // path records (13 words per path slot), 2 index queues, per-round counters
+    int wf_blocks_ = 0, wf_rounds_ = 1;                              // persistent grid (occupancy x SM count), launches of the path kernel per frame
+    uint32_t wf_spill_below_ = 0;
     Scene* scene_;
     NrcCache* nrc_;
     hpm_render_config cfg_;

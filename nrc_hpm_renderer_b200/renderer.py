@@ -190,6 +190,10 @@ class NrcHpmRenderer:
     def _fr(self, frame_random):
         return np.asarray(frame_random, dtype=np.float32).ctypes.data_as(C.POINTER(C.c_float))
 
+    def set_tracker_mode(self, mode: int):
+        """0 automatic, 1 one pixel per thread, 2 path regeneration -- identical results, different schedules"""
+        _lib.check(_lib.lib().hpm_renderer_set_tracker_mode(self._h, int(mode)))
+
     def pass_gen_rays(self, frame_random):
         fr = np.asarray(frame_random, dtype=np.float32)
         _lib.check(_lib.lib().hpm_pass_gen_rays(self._h, fr.ctypes.data_as(C.POINTER(C.c_float))))
