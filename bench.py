@@ -62,15 +62,18 @@ def synth_records(rng, n):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md).  The query process is started BEFORE the warm-up
+    (it needs a few hundred ms to print its first row) and every row is stamped on arrival; only rows that arrived inside the window
+    [begin(), end()] -- GPU under the bench load -- are reported."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
+        self.t0, self.t1 = 0.0, float("inf")
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -78,15 +81,24 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        if self.t1 == float("inf"):
+            self.end()
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for t, r in list(self.rows):
+            if not (self.t0 <= t <= self.t1):
+                continue
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
@@ -94,7 +106,8 @@ class ClockSampler:
                         reasons.add(name)
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm),
+                "window_s": round(self.t1 - self.t0, 3)}
 
 
 def peaks():
@@ -126,7 +139,10 @@ def run_reference(args):
         cmd = [binp, "bench", f"n_infer={N_INFER}", f"batch={TRAIN_BATCH}", f"batches={TRAIN_BATCHES}", f"frames={args.steps}", f"warmup={max(args.warmup, 3)}",
                "pos=0", "dir=0", "depth=6", f"sets={N_SETS}"]
         sampler = ClockSampler(); sampler.start()
+        time.sleep(0.3)                                                  # first nvidia-smi row
+        sampler.begin()
         res = subprocess.run(cmd, capture_output=True, text=True)
+        sampler.end()
         clocks = sampler.stop()
         line = [l for l in res.stdout.splitlines() if l.startswith("{")]
         if res.returncode != 0 or not line:
@@ -382,23 +398,37 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     warmup = max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                                # rows are only counted inside begin() .. end() below
     for i in range(warmup):
         step(i)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = _lib.lib().nrchpm_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev_k = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler.begin()
     e0.record(stream)
     for i in range(args.steps):
         step(warmup + i, ev_k[i])                      # dominant kernel, timed live on its own stream: the fused encode + MLP inference launch
     e1.record(stream)
     barrier()
     launches = _lib.lib().nrchpm_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
+    # a timed region shorter than ~0.7 s holds too few 50 ms clock samples: the SAME steps keep running (untimed, every rank the same count)
+    # until the load window is long enough, and the clocks are sampled over the whole window
+    t_ms = torch.tensor([ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    load_ms = float(t_ms.item())
+    extra_steps = 0 if load_ms >= 700.0 else int((700.0 - load_ms) / max(load_ms / args.steps, 1e-3)) + 1
+    for i in range(extra_steps):
+        step(warmup + args.steps + i)
+    barrier()
+    sampler.end()
+    clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = f"the {args.steps} timed steps" + (f" + {extra_steps} more of the same steps, untimed" if extra_steps else "")
     if world > 1 and peer:
         # the overlapped schedule has no serial inference launch to bracket: time the dominant kernel alone afterwards
         for i in range(args.steps):

@@ -166,14 +166,6 @@ typedef struct hpm_scene_desc {
 /* grid_host: dense 8-bit density (Texture3D::FromVDB semantics, one byte per voxel), copied to the device. */
 int hpm_scene_create(const hpm_scene_desc* desc, const uint8_t* grid_host, hpm_scene** out);
 int hpm_scene_destroy(hpm_scene* s);
-/* OPTIONAL, not the reference's algorithm: delta / ratio tracking against per-brick majorants
- * (bricks of brick_voxels^3 voxels walked with a DDA) instead of the global VOLUME_DENSITY_FACTOR of path_trace.glsl:154.
- * Same estimators in expectation (tests/test_gpu_tracker.py), 5.2x fewer density lookups on the bundled cloud at 8-voxel bricks --
- * but NOT faster on B200: the tracking kernels are bound by instruction issue, not by density fetches, and the DDA costs more
- * instructions than the null collisions it removes (gen_rays 0.46 ms -> 2.2 ms at 8 voxels, 1.3 ms at 16; profiles/r01_summary.md).
- * Experimental; the RNG consumption changes, so frames are not comparable sample by sample with the parity mode
- * (brick_voxels = 0, the default). */
-int hpm_scene_set_majorant_grid(hpm_scene* s, int brick_voxels);
 
 /* Constructor arguments of NrcHpmRenderer + the AppConfig fields its specialization constants use
  * (src/NrcHpmRenderer.cu:212-297, 908-1061; data/shader/include/nrc-constants.glsl:1-22). */

@@ -83,7 +83,6 @@ SIGNATURES = {
     "nrc_infer_and_train_host": (_I, [_P, _F, _F, _U32, _F, _F, _U32, _U32, _I, _F]),
     "hpm_scene_create": (_I, [C.POINTER(SceneDesc), _P, C.POINTER(_P)]),
     "hpm_scene_destroy": (_I, [_P]),
-    "hpm_scene_set_majorant_grid": (_I, [_P, _I]),
     "hpm_renderer_create": (_I, [_P, _P, C.POINTER(RenderConfig), _P, C.POINTER(_P)]),
     "hpm_renderer_destroy": (_I, [_P]),
     "hpm_renderer_set_camera": (_I, [_P, _F, _F]),

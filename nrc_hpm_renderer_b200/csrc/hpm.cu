@@ -31,19 +31,6 @@ Scene::Scene(const hpm_scene_desc& d, const uint8_t* grid_host) {
     dev_.dl_strength = d.dir_light_strength; dev_.pl_strength = d.point_strength; dev_.env_strength = d.env_strength;
 }
 
-void Scene::set_majorant_grid(int brick) {
-    NRCHPM_REQUIRE(brick >= 0 && brick <= 64, "majorant brick size must be 0 (off) .. 64 voxels");
-    NRCHPM_CUDA(cudaDeviceSynchronize());
-    if (brick == 0) { dev_.maj = nullptr; dev_.brick = 0; return; }
-    const int bx = (dev_.dim[0] + brick - 1) / brick, by = (dev_.dim[1] + brick - 1) / brick, bz = (dev_.dim[2] + brick - 1) / brick;
-    const size_t n = (size_t)bx * by * bz;
-    maj_.allocate(n);
-    hpm_build_majorants_kernel<<<(unsigned)((n + 127) / 128), 128>>>(grid_.ptr, dev_.dim[0], dev_.dim[1], dev_.dim[2], brick, bx, by, bz, maj_.ptr);
-    check_launch("hpm_build_majorants_kernel");
-    NRCHPM_CUDA(cudaDeviceSynchronize());
-    dev_.maj = maj_.ptr; dev_.brick = brick; dev_.bdim[0] = bx; dev_.bdim[1] = by; dev_.bdim[2] = bz;
-}
-
 Renderer::Renderer(Scene* scene, NrcCache* nrc, const hpm_render_config& cfg, cudaStream_t stream) : scene_(scene), nrc_(nrc), cfg_(cfg), stream_(stream) {
     NRCHPM_REQUIRE(scene, "renderer: null scene");
     NRCHPM_REQUIRE(cfg.width > 0 && cfg.height > 0, "renderer: bad resolution");
@@ -136,8 +123,7 @@ void Renderer::pass_gen_rays(const float fr[4]) {
     a.lookups = counters_.ptr;
     const uint32_t tw = hpmdev::kTileW, th = 128 / tw;
     const dim3 block(tw, th), grid((cfg_.x_end - cfg_.x_begin + tw - 1) / tw, (cfg_.height + th - 1) / th);
-    if (a.sc.maj) hpm_gen_rays_kernel<true><<<grid, block, 0, stream_>>>(a);
-    else hpm_gen_rays_kernel<false><<<grid, block, 0, stream_>>>(a);
+    hpm_gen_rays_kernel<<<grid, block, 0, stream_>>>(a);
     check_launch("hpm_gen_rays_kernel");
 }
 
@@ -148,7 +134,6 @@ void Renderer::set_tracker_mode(int mode) {
 }
 
 bool Renderer::use_wavefront() const {
-    if (scene_->dev().maj) return false;                       // the per-brick majorant mode exists in the pixel-per-thread kernels only
     if (cfg_.width > 65535u || cfg_.height > 65535u) return false;   // path records pack the pixel as x | y << 16
     // automatic = pixel per thread: measured faster on B200 at every configuration tried (profiles/r02_tracker_regeneration.md)
     return tracker_mode_ == 2;
@@ -226,8 +211,7 @@ void Renderer::pass_prep_train(const float fr[4]) {
         a.block_totals = block_totals_.ptr; a.n_blocks = n_blocks;
         a.train_in = cur_train_in(); a.train_target = cur_train_target(); a.lookups = counters_.ptr + 1;
         last_train_set_ = train_set_;
-        if (a.sc.maj) hpm_train_trace_kernel<true><<<(n_train_ + 127) / 128, 128, 0, stream_>>>(a);
-        else hpm_train_trace_kernel<false><<<(n_train_ + 127) / 128, 128, 0, stream_>>>(a);
+        hpm_train_trace_kernel<<<(n_train_ + 127) / 128, 128, 0, stream_>>>(a);
         check_launch("hpm_train_trace_kernel");
     }
 }
@@ -291,8 +275,7 @@ void Renderer::mc_render(const float fr[4], uint32_t path_length) {
     a.path_length = path_length; a.blend_factor = blend_factor_; a.output = output_.ptr; a.lookups = counters_.ptr;
     const uint32_t tw = hpmdev::kTileW, th = 128 / tw;
     const dim3 block(tw, th), grid((cfg_.x_end - cfg_.x_begin + tw - 1) / tw, (cfg_.height + th - 1) / th);
-    if (a.sc.maj) hpm_mc_render_kernel<true><<<grid, block, 0, stream_>>>(a);
-    else hpm_mc_render_kernel<false><<<grid, block, 0, stream_>>>(a);
+    hpm_mc_render_kernel<<<grid, block, 0, stream_>>>(a);
     check_launch("hpm_mc_render_kernel");
 }
 
@@ -363,7 +346,6 @@ int hpm_scene_create(const hpm_scene_desc* desc, const uint8_t* grid_host, hpm_s
     return guard([&] { NRCHPM_REQUIRE(desc && grid_host && out, "null argument"); *out = nullptr; *out = new hpm_scene(*desc, grid_host); });
 }
 int hpm_scene_destroy(hpm_scene* s) { return guard([&] { delete s; }); }
-int hpm_scene_set_majorant_grid(hpm_scene* s, int brick_voxels) { return guard([&] { NRCHPM_REQUIRE(s, "null scene"); s->impl.set_majorant_grid(brick_voxels); }); }
 int hpm_renderer_create(hpm_scene* scene, nrc_cache* nrc, const hpm_render_config* cfg, void* stream, hpm_renderer** out) {
     return guard([&] {
         NRCHPM_REQUIRE(scene && cfg && out, "null argument");

@@ -14,9 +14,8 @@ class Scene {
 public:
     Scene(const hpm_scene_desc& d, const uint8_t* grid_host);
     const SceneDev& dev() const { return dev_; }
-    void set_majorant_grid(int brick);            // 0: global majorant (the reference's algorithm); > 0: per-brick majorants
 private:
-    DeviceBuffer<uint8_t> grid_, maj_;
+    DeviceBuffer<uint8_t> grid_;
     SceneDev dev_{};
 };
 

@@ -65,7 +65,7 @@ __device__ __forceinline__ void warp_push(bool flag, uint32_t item, uint32_t* it
 }
 
 // end of a pixel's path (gen_rays.comp:44-51, 82-99 + prep_infer_rays.comp:26-46): images, query record, filter flag
-__device__ __forceinline__ void wf_finish(const WfArgs& a, const TrackerT<false>& c, uint32_t x, uint32_t y, V3 cur, V3 dir, V3 light, float factor, bool did_scatter) {
+__device__ __forceinline__ void wf_finish(const WfArgs& a, const Tracker& c, uint32_t x, uint32_t y, V3 cur, V3 dir, V3 light, float factor, bool did_scatter) {
     const uint32_t W = a.cfg.width, H = a.cfg.height;
     const size_t p = (size_t)y * W + x;
     if (a.origin) { a.origin[3 * p + 0] = cur.x; a.origin[3 * p + 1] = cur.y; a.origin[3 * p + 2] = cur.z; }
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(128) hpm_wf_primary_kernel(const __grid_consta
     const uint32_t W = a.cfg.width, H = a.cfg.height;
     const uint32_t x = a.cfg.x_begin + blockIdx.x * kTileW + threadIdx.x, y = blockIdx.y * (128 / kTileW) + threadIdx.y;
     __shared__ float s_lut[256];
-    TrackerT<false> c(a.sc, stage_density_lut(a.sc, s_lut));
+    Tracker c(a.sc, stage_density_lut(a.sc, s_lut));
     bool alive = false;
     V3 entry = mk(0, 0, 0), rd = mk(0, 0, 0);
     if (x < a.cfg.x_end && y < H) {
@@ -148,7 +148,7 @@ struct WfRound {
 __global__ void __launch_bounds__(128) hpm_wf_paths_kernel(const __grid_constant__ WfArgs a, const __grid_constant__ WfRound q) {
     using namespace hpmdev;
     __shared__ float s_lut[256];
-    TrackerT<false> c(a.sc, stage_density_lut(a.sc, s_lut));
+    Tracker c(a.sc, stage_density_lut(a.sc, s_lut));
     const uint32_t lane = threadIdx.x & 31, n = a.st.n;
     const uint32_t q_n = *q.in_count;
     uint32_t c_next = 0, c_end = 0;

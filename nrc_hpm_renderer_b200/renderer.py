@@ -59,10 +59,6 @@ class HpmScene:
         self._h = C.c_void_p()
         _lib.check(_lib.lib().hpm_scene_create(C.byref(desc), grid_u8.ctypes.data_as(C.c_void_p), C.byref(self._h)))
 
-    def set_majorant_grid(self, brick_voxels: int):
-        """0: the reference's global majorant (parity mode); > 0: per-brick majorants (optional, not sample-comparable)"""
-        _lib.check(_lib.lib().hpm_scene_set_majorant_grid(self._h, int(brick_voxels)))
-
     def Destroy(self):
         if self._h:
             _lib.check(_lib.lib().hpm_scene_destroy(self._h))

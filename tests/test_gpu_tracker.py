@@ -194,38 +194,6 @@ def test_frame_compact_equals_reference_mode(oracle_lib):
     assert np.any(imgs[0][2] != imgs[0][0])
 
 
-@pytest.mark.parametrize("scene_id,env", [(0, (0, 0, 0)), (4, (1, 1, 1))])
-def test_majorant_bricks_are_the_same_estimator(scene_id, env, oracle_lib):
-    """Optional per-brick majorants (hpm_scene_set_majorant_grid) change the random-number consumption, not the
-    expectation: the path tracer converges to the same image as with the reference's global majorant, with several times fewer
-    density lookups.  Tolerances are Monte-Carlo noise of 384 blended frames (block means, whole-image means)."""
-    from nrc_hpm_renderer_b200 import Camera, HpmSceneConfig
-    from nrc_hpm_renderer_b200 import renderer as R
-    grid = np.ascontiguousarray(golden("wdas_cloud_sixteenth_u8.npz")["data"])
-    W, H, FRAMES = 96, 64, 384
-    imgs, lookups = [], []
-    for brick in (0, 8):
-        scene = R.HpmScene(grid, HpmSceneConfig.preset(scene_id), env_color=env)
-        scene.set_majorant_grid(brick)
-        r = R.McHpmRenderer(W, H, 4, True, Camera(aspect=W / H), scene)
-        rng = np.random.default_rng(99)
-        n = 0
-        for _ in range(FRAMES):
-            r.Render(rng.random(4).astype(np.float32))
-            n += int(r.read(R.BUF_COUNTERS)[0])
-        imgs.append(r.GetImage().copy()); lookups.append(n)
-        r.Destroy(); scene.Destroy()
-    a, b = imgs
-    assert np.isfinite(a).all() and np.isfinite(b).all()
-    assert abs(b[..., 3].mean() - a[..., 3].mean()) <= 0.004                              # opacity (fraction of frames that scattered)
-    assert abs(b[..., :3].mean() - a[..., :3].mean()) <= 0.02 * a[..., :3].mean()        # radiance
-    blk = lambda im: im.reshape(H // 8, 8, W // 8, 8, 4).mean((1, 3))
-    da = blk(b)[..., 0] - blk(a)[..., 0]
-    assert np.sqrt((da ** 2).mean()) <= 0.06 * blk(a)[..., 0].mean()                      # block means agree to noise
-    assert np.abs(blk(b)[..., 3] - blk(a)[..., 3]).max() <= 0.03
-    assert lookups[1] < 0.5 * lookups[0], lookups                                         # what the mode is for
-
-
 def test_tracker_logf_is_the_library_logf_on_every_reachable_argument():
     """The Woodcock loops call a branch-free logf (no denormal / zero / inf / NaN paths); it must equal CUDA's logf bit for bit on
     all 2^23 arguments 1 - u the RNG can produce."""
