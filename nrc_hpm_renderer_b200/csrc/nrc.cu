@@ -1143,14 +1143,22 @@ void NrcCache::ensure_pipeline(uint32_t n_chunks) {
         pipe_events_.push_back(e);
     }
 }
-// queues the chunked H2D -> kernel -> D2H pipeline; returns without waiting
-void NrcCache::queue_inference_pipeline(const __half* params, const float* h_in, float* h_out, uint32_t n, uint32_t chunk, uint32_t n_chunks) {
+// queues the chunked H2D -> kernel -> D2H pipeline; returns without waiting.  copies_queued: the H2D copies and their events are
+// already on copy_in_stream_ (queue_inference_copies_in)
+void NrcCache::queue_inference_copies_in(const float* h_in, uint32_t n, uint32_t chunk, uint32_t n_chunks) {
     for (uint32_t c = 0; c < n_chunks; c++) {
         const uint32_t o = c * chunk, m = std::min(chunk, n - o);
         NRCHPM_CUDA(cudaMemcpyAsync(host_in_.ptr + (size_t)o * 5, h_in + (size_t)o * 5, (size_t)m * 5 * sizeof(float), cudaMemcpyHostToDevice, copy_in_stream_));
         NRCHPM_CUDA(cudaEventRecord(pipe_events_[2 * c], copy_in_stream_));
+    }
+}
+void NrcCache::queue_inference_pipeline(const __half* params, const float* h_in, float* h_out, uint32_t n, uint32_t chunk, uint32_t n_chunks, bool copies_queued,
+                                        uint32_t max_ctas) {
+    if (!copies_queued) queue_inference_copies_in(h_in, n, chunk, n_chunks);
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        const uint32_t o = c * chunk, m = std::min(chunk, n - o);
         NRCHPM_CUDA(cudaStreamWaitEvent(compute_stream_, pipe_events_[2 * c], 0));
-        inference_with(params, host_in_.ptr + (size_t)o * 5, host_out_.ptr + (size_t)o * 3, m, nullptr, nullptr, compute_stream_, 0);
+        inference_with(params, host_in_.ptr + (size_t)o * 5, host_out_.ptr + (size_t)o * 3, m, nullptr, nullptr, compute_stream_, max_ctas);
         NRCHPM_CUDA(cudaEventRecord(pipe_events_[2 * c + 1], compute_stream_));
         NRCHPM_CUDA(cudaStreamWaitEvent(copy_out_stream_, pipe_events_[2 * c + 1], 0));
         NRCHPM_CUDA(cudaMemcpyAsync(h_out + (size_t)o * 3, host_out_.ptr + (size_t)o * 3, (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToHost, copy_out_stream_));
@@ -1168,7 +1176,7 @@ void NrcCache::inference_host(const float* h_in, float* h_out, uint32_t n, bool 
     NRCHPM_CUDA(cudaStreamWaitEvent(compute_stream_, ev_prev, 0));
     NRCHPM_CUDA(cudaStreamWaitEvent(copy_in_stream_, ev_prev, 0));
     if (use_ema) wait_ema(compute_stream_);
-    queue_inference_pipeline(use_ema ? ema16_.ptr : w16_.ptr, h_in, h_out, n, chunk, n_chunks);
+    queue_inference_pipeline(use_ema ? ema16_.ptr : w16_.ptr, h_in, h_out, n, chunk, n_chunks, false, 0);
     NRCHPM_CUDA(cudaStreamSynchronize(copy_out_stream_));
 }
 void NrcCache::training_step_host(const float* h_in, const float* h_tgt, uint32_t B, float* loss_out) {
@@ -1214,9 +1222,13 @@ void NrcCache::infer_and_train_host(const float* h_in, float* h_out, uint32_t n,
         NRCHPM_CUDA(cudaMemcpyAsync(host_tgt_.ptr, h_tgt, T * 3 * sizeof(float), cudaMemcpyHostToDevice, copy_in_stream_));
         NRCHPM_CUDA(cudaEventRecord(ev_train, copy_in_stream_));
     }
+    // PCIe is the scarce resource of this call (20 B in + 12 B out per record): every H2D copy is queued before the host spends its
+    // time on the training launches
+    if (n) queue_inference_copies_in(h_in, n, chunk, n_chunks);
     // Training goes FIRST on the device: its records are small and have landed long before the first inference chunk has crossed
     // PCIe, and the persistent inference launches cannot share an SM with the training kernels (TMEM and registers), so interleaving
-    // the two only makes every training kernel wait for a whole chunk to drain (measured: 1.81 ms; training first: see profiles/).
+    // the two only makes every training kernel wait for a whole chunk to drain (measured: 1.81 ms; training first: see profiles/;
+    // inference chunks capped to 88..124 SMs NEXT TO the training steps: 1.31-1.52 ms against 1.26, profiles/r02_e2e_knobs.jsonl).
     // The inference kernels wait for the last optimizer step; their H2D copies do not.  Inference still evaluates the snapshot.
     if (train) {
         NRCHPM_CUDA(cudaStreamWaitEvent(ts, ev_train, 0));
@@ -1238,7 +1250,7 @@ void NrcCache::infer_and_train_host(const float* h_in, float* h_out, uint32_t n,
     }
     if (n) {
         if (!overlap && use_ema) wait_ema(compute_stream_);
-        queue_inference_pipeline(overlap ? infer_snapshot_.ptr : (use_ema ? ema16_.ptr : w16_.ptr), h_in, h_out, n, chunk, n_chunks);
+        queue_inference_pipeline(overlap ? infer_snapshot_.ptr : (use_ema ? ema16_.ptr : w16_.ptr), h_in, h_out, n, chunk, n_chunks, true, 0);
     }
     // later work on the cache's own stream is ordered behind this call
     NRCHPM_CUDA(cudaEventRecord(ev_done, compute_stream_));

@@ -90,7 +90,8 @@ private:
     void training_step_three_kernels(const float* d_in, const float* d_target, uint32_t B, cudaStream_t s);
     void launch_shape(uint32_t tiles, uint32_t& grid, uint32_t& threads) const;
     void ensure_pipeline(uint32_t n_chunks);
-    void queue_inference_pipeline(const __half* params, const float* h_in, float* h_out, uint32_t n, uint32_t chunk, uint32_t n_chunks);
+    void queue_inference_copies_in(const float* h_in, uint32_t n, uint32_t chunk, uint32_t n_chunks);
+    void queue_inference_pipeline(const __half* params, const float* h_in, float* h_out, uint32_t n, uint32_t chunk, uint32_t n_chunks, bool copies_queued, uint32_t max_ctas);
     void inference_with(const __half* params, const float* d_in, float* d_out, uint32_t n, const uint32_t* d_indices, const uint32_t* d_count, cudaStream_t s, uint32_t max_ctas);
     void infer_and_train_overlapped();
 
