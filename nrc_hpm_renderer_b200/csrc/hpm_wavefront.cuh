@@ -145,7 +145,7 @@ struct WfRound {
     uint32_t spill_below;                                                       // 0: run every path to its end
 };
 
-__global__ void __launch_bounds__(128) hpm_wf_paths_kernel(const __grid_constant__ WfArgs a, const __grid_constant__ WfRound q) {
+__global__ void __launch_bounds__(128, 8) hpm_wf_paths_kernel(const __grid_constant__ WfArgs a, const __grid_constant__ WfRound q) {
     using namespace hpmdev;
     __shared__ float s_lut[256];
     Tracker c(a.sc, stage_density_lut(a.sc, s_lut));

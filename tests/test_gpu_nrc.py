@@ -258,6 +258,42 @@ def test_indexed_inference_matches_dense():
     assert np.all(s[mask] == -1.0)
 
 
+@pytest.mark.parametrize("width", [64, 128])
+def test_empty_and_ragged_batches(width):
+    """Edge sizes of Inference(): no records, one record, one short of / one past a 128-record tile, a ragged multi-tile batch, and an
+    empty compaction list.  A record's result must not depend on the batch it sits in (bit for bit against the same rows of one large
+    batch), rows past the batch must stay untouched, and n = 0 must be a no-op instead of an error
+    (reference: src/NeuralRadianceCache.cu:100-118 loops over however many batches the filter leaves, possibly none)."""
+    import torch
+    from nrc_hpm_renderer_b200 import AppConfig, nrc as N
+    app = AppConfig.default(); app.nn_width = width
+    c = N.NeuralRadianceCache(app)
+    c.set_ema(c.get_params(N.MASTER))
+    rng = np.random.default_rng(11)
+    n_all = 148 * 128 * 2 + 77
+    rec = dev(rng.random((n_all, 5), dtype=np.float32))
+    full = torch.zeros((n_all, 3), dtype=torch.float32, device="cuda")
+    c.inference(rec, full, n_all)
+    torch.cuda.synchronize()
+    ref = full.cpu().numpy()
+    assert np.any(ref != 0)
+    for n in (0, 1, 127, 128, 129, 1000, 148 * 128 + 1):
+        out = torch.full((n_all, 3), -7.0, dtype=torch.float32, device="cuda")
+        c.inference(rec, out, n)
+        torch.cuda.synchronize()
+        o = out.cpu().numpy()
+        assert np.array_equal(o[:n], ref[:n]), n
+        assert np.all(o[n:] == -7.0), n
+    # compacted inference with an empty list: nothing is written
+    out = torch.full((n_all, 3), -7.0, dtype=torch.float32, device="cuda")
+    idx = torch.zeros(16, dtype=torch.int32, device="cuda"); cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    c.inference_indexed(rec, out, idx, cnt, n_all)
+    torch.cuda.synchronize()
+    assert np.all(out.cpu().numpy() == -7.0)
+    # host entry point with no records
+    assert c.inference_host(np.zeros((0, 5), np.float32), use_ema=True).shape == (0, 3)
+
+
 def test_host_entry_points_and_errors():
     from nrc_hpm_renderer_b200 import AppConfig, nrc as N, _lib
     c = N.NeuralRadianceCache(AppConfig.default())
