@@ -8,7 +8,10 @@
 #include "mini_json.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <string>
 #include <cstdlib>
 #include <cstring>
 #include <random>
@@ -719,15 +722,21 @@ void NrcCache::optimizer_step(cudaStream_t s) {
         // measured it as extra CTAs of the next training launch, on the 20 SMs a 2^14 batch leaves idle: 20 SMs stream the 85 MB in
         // 85 us, longer than the training CTAs' 48 us -- 1.08 instead of 0.98 ms per bench step.)
         NRCHPM_CUDA(cudaEventRecord(adam_done_, s));
-        NRCHPM_CUDA(cudaStreamWaitEvent(ema_stream_, adam_done_, 0));
-        if (ema_gate_) { NRCHPM_CUDA(cudaStreamWaitEvent(ema_stream_, ema_gate_, 0)); ema_gate_ = nullptr; }   // a snapshot copy still reads the EMA weights
-        launch_hot(nrc_grid_ema_kernel, (unsigned)sm_count_, 256, 0, ema_stream_, a);
-        check_launch("nrc_grid_ema_kernel");
-        NRCHPM_CUDA(cudaEventRecord(ema_done_, ema_stream_));
-        ema_in_flight_ = true;
+        launch_ema(a);
     }
     grid_grad_dirty_ = false;       // the optimizer re-zeroes every encoding gradient it consumed
     grads_pending_ = false;
+}
+
+// (Measured for the host path: launching the LAST step's pass behind the inference kernels, which read a snapshot and cannot share an SM
+// with its 148 resident blocks, changes nothing -- 1.23-1.25 ms either way, profiles/r02_e2e_knobs.jsonl.)
+void NrcCache::launch_ema(const OptArgs& a) {
+    NRCHPM_CUDA(cudaStreamWaitEvent(ema_stream_, adam_done_, 0));
+    if (ema_gate_) { NRCHPM_CUDA(cudaStreamWaitEvent(ema_stream_, ema_gate_, 0)); ema_gate_ = nullptr; }   // a snapshot copy still reads the EMA weights
+    launch_hot(nrc_grid_ema_kernel, (unsigned)sm_count_, 256, 0, ema_stream_, a);
+    check_launch("nrc_grid_ema_kernel");
+    NRCHPM_CUDA(cudaEventRecord(ema_done_, ema_stream_));
+    ema_in_flight_ = true;
 }
 
 // the EMA weights are complete once the last EMA pass has finished: every reader of ema16_ orders itself behind it
@@ -1138,37 +1147,52 @@ void NrcCache::ensure_pipeline(uint32_t n_chunks) {
         NRCHPM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         NRCHPM_CUDA(cudaStreamCreateWithPriority(&train_stream_, cudaStreamNonBlocking, prio_hi));
     }
-    while (pipe_events_.size() < 2 * (size_t)n_chunks + 5) {
+    while (pipe_events_.size() < 2 * (size_t)n_chunks + 6) {
         cudaEvent_t e; NRCHPM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         pipe_events_.push_back(e);
     }
 }
-// queues the chunked H2D -> kernel -> D2H pipeline; returns without waiting.  copies_queued: the H2D copies and their events are
-// already on copy_in_stream_ (queue_inference_copies_in)
-void NrcCache::queue_inference_copies_in(const float* h_in, uint32_t n, uint32_t chunk, uint32_t n_chunks) {
-    for (uint32_t c = 0; c < n_chunks; c++) {
-        const uint32_t o = c * chunk, m = std::min(chunk, n - o);
+// queues the chunked H2D -> kernel -> D2H pipeline; returns without waiting.  `off` holds the chunk boundaries (record indices, off[0] = 0,
+// off.back() = n); copies_queued: the H2D copies and their events are already on copy_in_stream_ (queue_inference_copies_in)
+// development aid (NRCHPM_E2E_TRACE=1): timing events at the hand-over points of the host pipeline, printed to stderr as one JSON line per call
+void NrcCache::trace_mark(const char* name, cudaStream_t s) {
+    if (!trace_on_) return;
+    cudaEvent_t e; NRCHPM_CUDA(cudaEventCreate(&e)); NRCHPM_CUDA(cudaEventRecord(e, s));
+    trace_.emplace_back(name, e);
+}
+static std::vector<uint32_t> uniform_chunks(uint32_t n, uint32_t chunk) {
+    std::vector<uint32_t> off{0u};
+    while (off.back() < n) off.push_back(std::min(n, off.back() + chunk));
+    return off;
+}
+void NrcCache::queue_inference_copies_in(const float* h_in, const std::vector<uint32_t>& off) {
+    for (size_t c = 0; c + 1 < off.size(); c++) {
+        const uint32_t o = off[c], m = off[c + 1] - o;
         NRCHPM_CUDA(cudaMemcpyAsync(host_in_.ptr + (size_t)o * 5, h_in + (size_t)o * 5, (size_t)m * 5 * sizeof(float), cudaMemcpyHostToDevice, copy_in_stream_));
         NRCHPM_CUDA(cudaEventRecord(pipe_events_[2 * c], copy_in_stream_));
+        trace_mark("h2d", copy_in_stream_);
     }
 }
-void NrcCache::queue_inference_pipeline(const __half* params, const float* h_in, float* h_out, uint32_t n, uint32_t chunk, uint32_t n_chunks, bool copies_queued,
-                                        uint32_t max_ctas) {
-    if (!copies_queued) queue_inference_copies_in(h_in, n, chunk, n_chunks);
-    for (uint32_t c = 0; c < n_chunks; c++) {
-        const uint32_t o = c * chunk, m = std::min(chunk, n - o);
+void NrcCache::queue_inference_pipeline(const __half* params, const float* h_in, float* h_out, const std::vector<uint32_t>& off, bool copies_queued) {
+    if (!copies_queued) queue_inference_copies_in(h_in, off);
+    for (size_t c = 0; c + 1 < off.size(); c++) {
+        const uint32_t o = off[c], m = off[c + 1] - o;
         NRCHPM_CUDA(cudaStreamWaitEvent(compute_stream_, pipe_events_[2 * c], 0));
-        inference_with(params, host_in_.ptr + (size_t)o * 5, host_out_.ptr + (size_t)o * 3, m, nullptr, nullptr, compute_stream_, max_ctas);
+        trace_mark("inf_begin", compute_stream_);
+        inference_with(params, host_in_.ptr + (size_t)o * 5, host_out_.ptr + (size_t)o * 3, m, nullptr, nullptr, compute_stream_, 0);
         NRCHPM_CUDA(cudaEventRecord(pipe_events_[2 * c + 1], compute_stream_));
+        trace_mark("inf_end", compute_stream_);
         NRCHPM_CUDA(cudaStreamWaitEvent(copy_out_stream_, pipe_events_[2 * c + 1], 0));
         NRCHPM_CUDA(cudaMemcpyAsync(h_out + (size_t)o * 3, host_out_.ptr + (size_t)o * 3, (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToHost, copy_out_stream_));
+        trace_mark("d2h", copy_out_stream_);
     }
 }
 void NrcCache::inference_host(const float* h_in, float* h_out, uint32_t n, bool use_ema) {
     if (n == 0) return;
     host_in_.ensure((size_t)n * 5); host_out_.ensure((size_t)n * 3);
     const uint32_t chunk = (uint32_t)sm_count_ * 2 * 2 * 4 * kTile;       // 4 tiles per resident warpgroup
-    const uint32_t n_chunks = (n + chunk - 1) / chunk;
+    const std::vector<uint32_t> off = uniform_chunks(n, chunk);
+    const uint32_t n_chunks = (uint32_t)off.size() - 1;
     ensure_pipeline(n_chunks);
     // everything already queued on the cache's stream (e.g. a training step that changed the weights) comes first
     cudaEvent_t ev_prev = pipe_events_[2 * (size_t)n_chunks];
@@ -1176,7 +1200,7 @@ void NrcCache::inference_host(const float* h_in, float* h_out, uint32_t n, bool 
     NRCHPM_CUDA(cudaStreamWaitEvent(compute_stream_, ev_prev, 0));
     NRCHPM_CUDA(cudaStreamWaitEvent(copy_in_stream_, ev_prev, 0));
     if (use_ema) wait_ema(compute_stream_);
-    queue_inference_pipeline(use_ema ? ema16_.ptr : w16_.ptr, h_in, h_out, n, chunk, n_chunks, false, 0);
+    queue_inference_pipeline(use_ema ? ema16_.ptr : w16_.ptr, h_in, h_out, off, false);
     NRCHPM_CUDA(cudaStreamSynchronize(copy_out_stream_));
 }
 void NrcCache::training_step_host(const float* h_in, const float* h_tgt, uint32_t B, float* loss_out) {
@@ -1199,32 +1223,41 @@ void NrcCache::infer_and_train_host(const float* h_in, float* h_out, uint32_t n,
     if (n) { host_in_.ensure((size_t)n * 5); host_out_.ensure((size_t)n * 3); }
     const size_t T = (size_t)B * n_batches;
     if (train) { host_tin_.ensure(T * 5); host_tgt_.ensure(T * 3); ensure_train_scratch(B); }
-    uint32_t chunk = (uint32_t)sm_count_ * 2 * 2 * 8 * kTile;          // 8 tiles per resident warpgroup: 4 chunks for a 1080p frame
+    // 4 chunks for a 1080p frame (8 tiles per resident warpgroup).  Measured alternatives (profiles/r02_e2e_knobs.jsonl): 8 / 16 uniform
+    // chunks 1.29 / 1.38 ms, a large first chunk and shrinking later ones (40/25/17/11/7 %) 1.25, two or three chunks 1.27-1.45, against 1.24.
+    uint32_t chunk = (uint32_t)sm_count_ * 2 * 2 * 8 * kTile;
     if (const char* v = std::getenv("NRCHPM_E2E_CHUNK_TILES")) chunk = (uint32_t)sm_count_ * 2 * 2 * (uint32_t)std::max(1, std::atoi(v)) * kTile;   // experiment knob
-    const uint32_t n_chunks = (n + chunk - 1) / chunk;
+    const std::vector<uint32_t> off = uniform_chunks(n, chunk);
+    const uint32_t n_chunks = (uint32_t)off.size() - 1;
     ensure_pipeline(n_chunks);
     const size_t e0 = 2 * (size_t)n_chunks;
-    cudaEvent_t ev_prev = pipe_events_[e0], ev_train = pipe_events_[e0 + 1], ev_done = pipe_events_[e0 + 2], ev_snap = pipe_events_[e0 + 3], ev_trained = pipe_events_[e0 + 4];
+    cudaEvent_t ev_prev = pipe_events_[e0], ev_train = pipe_events_[e0 + 1], ev_done = pipe_events_[e0 + 2], ev_snap = pipe_events_[e0 + 3], ev_trained = pipe_events_[e0 + 4], ev_loss = pipe_events_[e0 + 5];
     const bool overlap = train && n > 0;
     cudaStream_t ts = overlap ? train_stream_ : compute_stream_;
+    static const bool trace_env = std::getenv("NRCHPM_E2E_TRACE") != nullptr;
+    trace_on_ = trace_env;
+    const auto host_t0 = std::chrono::steady_clock::now();
     NRCHPM_CUDA(cudaEventRecord(ev_prev, stream_));
     NRCHPM_CUDA(cudaStreamWaitEvent(compute_stream_, ev_prev, 0));
     NRCHPM_CUDA(cudaStreamWaitEvent(copy_in_stream_, ev_prev, 0));
+    trace_mark("start", copy_in_stream_);
     if (overlap) {
         infer_snapshot_.ensure(n_params_);
         if (use_ema) wait_ema(compute_stream_);
         NRCHPM_CUDA(cudaMemcpyAsync(infer_snapshot_.ptr, use_ema ? ema16_.ptr : w16_.ptr, n_params_ * sizeof(__half), cudaMemcpyDeviceToDevice, compute_stream_));
         NRCHPM_CUDA(cudaEventRecord(ev_snap, compute_stream_));
+        trace_mark("snapshot", compute_stream_);
         NRCHPM_CUDA(cudaStreamWaitEvent(train_stream_, ev_snap, 0));        // training overwrites what the snapshot copy reads
     }
     if (train) {
         NRCHPM_CUDA(cudaMemcpyAsync(host_tin_.ptr, h_tin, T * 5 * sizeof(float), cudaMemcpyHostToDevice, copy_in_stream_));
         NRCHPM_CUDA(cudaMemcpyAsync(host_tgt_.ptr, h_tgt, T * 3 * sizeof(float), cudaMemcpyHostToDevice, copy_in_stream_));
         NRCHPM_CUDA(cudaEventRecord(ev_train, copy_in_stream_));
+        trace_mark("train_h2d", copy_in_stream_);
     }
     // PCIe is the scarce resource of this call (20 B in + 12 B out per record): every H2D copy is queued before the host spends its
     // time on the training launches
-    if (n) queue_inference_copies_in(h_in, n, chunk, n_chunks);
+    if (n) queue_inference_copies_in(h_in, off);
     // Training goes FIRST on the device: its records are small and have landed long before the first inference chunk has crossed
     // PCIe, and the persistent inference launches cannot share an SM with the training kernels (TMEM and registers), so interleaving
     // the two only makes every training kernel wait for a whole chunk to drain (measured: 1.81 ms; training first: see profiles/;
@@ -1232,7 +1265,9 @@ void NrcCache::infer_and_train_host(const float* h_in, float* h_out, uint32_t n,
     // The inference kernels wait for the last optimizer step; their H2D copies do not.  Inference still evaluates the snapshot.
     if (train) {
         NRCHPM_CUDA(cudaStreamWaitEvent(ts, ev_train, 0));
+        trace_mark("train_begin", ts);
         for (uint32_t b = 0; b < n_batches; b++) {
+            if (b) trace_mark("train_step", ts);
             if (peer_world_ >= 2) {      // data-parallel replica: mean gradient over the ranks
                 training_step(host_tin_.ptr + (size_t)b * B * 5, host_tgt_.ptr + (size_t)b * B * 3, B, false, ts);
                 peer_exchange(ts);
@@ -1241,22 +1276,41 @@ void NrcCache::infer_and_train_host(const float* h_in, float* h_out, uint32_t n,
                 training_step(host_tin_.ptr + (size_t)b * B * 5, host_tgt_.ptr + (size_t)b * B * 3, B, true, ts);
             }
         }
+        trace_mark("train_end", ts);
+        if (overlap) {
+            // recorded BEFORE the loss read-back: the inference kernels wait for the optimizer, not for a copy-engine round trip
+            NRCHPM_CUDA(cudaEventRecord(ev_trained, train_stream_));
+            NRCHPM_CUDA(cudaStreamWaitEvent(compute_stream_, ev_trained, 0));
+        }
         if (!loss_pinned_) NRCHPM_CUDA(cudaMallocHost((void**)&loss_pinned_, sizeof(float)));   // pageable memory would make this copy block the host
         NRCHPM_CUDA(cudaMemcpyAsync(loss_pinned_, loss_dev_.ptr, sizeof(float), cudaMemcpyDeviceToHost, ts));
         if (overlap) {
-            NRCHPM_CUDA(cudaEventRecord(ev_trained, train_stream_));
-            NRCHPM_CUDA(cudaStreamWaitEvent(compute_stream_, ev_trained, 0));
+            NRCHPM_CUDA(cudaEventRecord(ev_loss, train_stream_));
+            NRCHPM_CUDA(cudaStreamWaitEvent(copy_out_stream_, ev_loss, 0));                    // the host's final wait on copy_out_stream_ covers the loss
         }
     }
     if (n) {
         if (!overlap && use_ema) wait_ema(compute_stream_);
-        queue_inference_pipeline(overlap ? infer_snapshot_.ptr : (use_ema ? ema16_.ptr : w16_.ptr), h_in, h_out, n, chunk, n_chunks, true, 0);
+        queue_inference_pipeline(overlap ? infer_snapshot_.ptr : (use_ema ? ema16_.ptr : w16_.ptr), h_in, h_out, off, true);
     }
     // later work on the cache's own stream is ordered behind this call
     NRCHPM_CUDA(cudaEventRecord(ev_done, compute_stream_));
     NRCHPM_CUDA(cudaStreamWaitEvent(stream_, ev_done, 0));
+    const auto host_t1 = std::chrono::steady_clock::now();
     NRCHPM_CUDA(cudaStreamSynchronize(compute_stream_));
     NRCHPM_CUDA(cudaStreamSynchronize(copy_out_stream_));
     if (train) { loss_host_ = *loss_pinned_; loss_valid_ = true; if (loss_out) *loss_out = loss_host_; }
+    if (trace_on_) {
+        const auto host_t2 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "{\"e2e_trace_us\": {\"host_enqueue\": %.1f, \"host_total\": %.1f, \"events\": [", std::chrono::duration<double, std::micro>(host_t1 - host_t0).count(),
+                     std::chrono::duration<double, std::micro>(host_t2 - host_t0).count());
+        for (size_t i = 0; i < trace_.size(); i++) {
+            float ms = 0; cudaEventSynchronize(trace_[i].second); cudaEventElapsedTime(&ms, trace_[0].second, trace_[i].second);
+            std::fprintf(stderr, "%s[\"%s\", %.1f]", i ? ", " : "", trace_[i].first.c_str(), ms * 1e3f);
+        }
+        std::fprintf(stderr, "]}}\n");
+        for (auto& t : trace_) cudaEventDestroy(t.second);
+        trace_.clear(); trace_on_ = false;
+    }
 }
 }  // namespace nrchpm

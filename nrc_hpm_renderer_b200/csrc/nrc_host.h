@@ -27,6 +27,8 @@ struct NrcConfig {
 
 constexpr uint32_t kMaxDwChunks = 256;      // weight-gradient partials: 32 batch chunks up to 1024 tiles (the reference's 2^14 batches), up to 256 beyond
 
+struct OptArgs;          // nrc_kernels.cuh
+
 class NrcCache {
 public:
     NrcCache(const NrcConfig& cfg, uint64_t seed);
@@ -90,8 +92,10 @@ private:
     void training_step_three_kernels(const float* d_in, const float* d_target, uint32_t B, cudaStream_t s);
     void launch_shape(uint32_t tiles, uint32_t& grid, uint32_t& threads) const;
     void ensure_pipeline(uint32_t n_chunks);
-    void queue_inference_copies_in(const float* h_in, uint32_t n, uint32_t chunk, uint32_t n_chunks);
-    void queue_inference_pipeline(const __half* params, const float* h_in, float* h_out, uint32_t n, uint32_t chunk, uint32_t n_chunks, bool copies_queued, uint32_t max_ctas);
+    void trace_mark(const char* name, cudaStream_t s);
+    void launch_ema(const OptArgs& a);
+    void queue_inference_copies_in(const float* h_in, const std::vector<uint32_t>& chunk_offsets);
+    void queue_inference_pipeline(const __half* params, const float* h_in, float* h_out, const std::vector<uint32_t>& chunk_offsets, bool copies_queued);
     void inference_with(const __half* params, const float* d_in, float* d_out, uint32_t n, const uint32_t* d_indices, const uint32_t* d_count, cudaStream_t s, uint32_t max_ctas);
     void infer_and_train_overlapped();
 
@@ -161,6 +165,8 @@ private:
     DeviceBuffer<unsigned int> peer_done_;
     uint32_t infer_max_ctas_ = 0;                    // 0: the full persistent grid (2 CTAs per SM)
     std::vector<cudaEvent_t> pipe_events_;
+    bool trace_on_ = false;                              // NRCHPM_E2E_TRACE: timing events of one nrc_infer_and_train_host call
+    std::vector<std::pair<std::string, cudaEvent_t>> trace_;
 };
 
 }  // namespace nrchpm
