@@ -58,6 +58,17 @@ int nrc_destroy(nrc_cache* c);
  * float[batch_count*batch_size][5], train_target float[...][3].  infer_count must be a multiple of 16. */
 int nrc_init(nrc_cache* c, uint32_t infer_count, float* d_infer_in, float* d_infer_out, float* d_train_in,
              float* d_train_target, void* start_semaphore, void* finished_semaphore, void* stream);
+/* Vulkan <-> CUDA interop of the reference, Linux flavour.  The reference exports its four NRC record buffers with
+ * VK_EXTERNAL_MEMORY_HANDLE_TYPE_OPAQUE_FD_BIT and imports + maps them in NrcHpmRenderer::CreateNrcBuffers (src/NrcHpmRenderer.cu:700-821);
+ * its two semaphores are exported with vkGetSemaphoreFdKHR and imported in CreateSyncObjects (:644-690).  These helpers are that import
+ * step: the returned device pointer / semaphore go straight into nrc_init.  The fd is owned by CUDA after a successful import (do not
+ * close it).  UNTESTED against a Vulkan device: this image has none; the error paths are under test. */
+typedef struct nrchpm_external_buffer nrchpm_external_buffer;
+int nrchpm_import_external_buffer(int opaque_fd, size_t bytes, nrchpm_external_buffer** out, void** d_ptr_out);
+int nrchpm_release_external_buffer(nrchpm_external_buffer* b);              /* NrcHpmRenderer::Destroy (:355-...) cudaDestroyExternalMemory */
+int nrchpm_import_external_semaphore(int opaque_fd, void** cuda_external_semaphore_out);
+int nrchpm_release_external_semaphore(void* cuda_external_semaphore);
+
 /* en::NeuralRadianceCache::InferAndTrain / Inference / Train (src/NeuralRadianceCache.cu:97-156).
  * infer_filter is a HOST pointer, one uint32 per inference batch (NULL = run every batch). */
 int nrc_infer_and_train(nrc_cache* c, const uint32_t* infer_filter_host, int train);

@@ -50,6 +50,10 @@ SIGNATURES = {
     "nrc_create": (_I, [C.c_char_p, _U64, C.POINTER(_P)]),
     "nrc_destroy": (_I, [_P]),
     "nrc_init": (_I, [_P, _U32, _P, _P, _P, _P, _P, _P, _P]),
+    "nrchpm_import_external_buffer": (_I, [_I, _SZ, C.POINTER(_P), C.POINTER(_P)]),
+    "nrchpm_release_external_buffer": (_I, [_P]),
+    "nrchpm_import_external_semaphore": (_I, [_I, C.POINTER(_P)]),
+    "nrchpm_release_external_semaphore": (_I, [_P]),
     "nrc_infer_and_train": (_I, [_P, C.POINTER(_U32), _I]),
     "nrc_inference": (_I, [_P, C.POINTER(_U32)]),
     "nrc_train": (_I, [_P]),

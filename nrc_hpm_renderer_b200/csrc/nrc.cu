@@ -990,6 +990,48 @@ int nrc_gradient_buffers(nrc_cache* c, float** mlp, void** enc) {
 int nrc_encode_batch(nrc_cache* c, const float* d_in, uint32_t n, int use_ema, void* d_out, void* stream) {
     return guard([&] { NRCHPM_REQUIRE(c && d_in && d_out, "null argument"); c->impl.encode(d_in, n, use_ema != 0, d_out, (cudaStream_t)stream); });
 }
+// ---- Vulkan interop (reference src/NrcHpmRenderer.cu:644-690, 700-821): import of exported buffers / semaphores by opaque fd
+struct nrchpm_external_buffer { cudaExternalMemory_t mem = nullptr; void* ptr = nullptr; };
+int nrchpm_import_external_buffer(int fd, size_t bytes, nrchpm_external_buffer** out, void** d_ptr_out) {
+    return guard([&] {
+        NRCHPM_REQUIRE(out && d_ptr_out, "null argument");
+        *out = nullptr; *d_ptr_out = nullptr;
+        NRCHPM_REQUIRE(fd >= 0 && bytes > 0, "external buffer: bad file descriptor or size");
+        cudaExternalMemoryHandleDesc hd{};
+        hd.type = cudaExternalMemoryHandleTypeOpaqueFd; hd.handle.fd = fd; hd.size = bytes;
+        nrchpm_external_buffer b;
+        NRCHPM_CUDA(cudaImportExternalMemory(&b.mem, &hd));
+        cudaExternalMemoryBufferDesc bd{};
+        bd.offset = 0; bd.size = bytes; bd.flags = 0;
+        const cudaError_t e = cudaExternalMemoryGetMappedBuffer(&b.ptr, b.mem, &bd);
+        if (e != cudaSuccess) { cudaDestroyExternalMemory(b.mem); NRCHPM_CUDA(e); }
+        *out = new nrchpm_external_buffer(b); *d_ptr_out = b.ptr;
+    });
+}
+int nrchpm_release_external_buffer(nrchpm_external_buffer* b) {
+    return guard([&] {
+        if (!b) return;
+        if (b->ptr) cudaFree(b->ptr);                      // a mapped buffer is released with cudaFree, then the memory object
+        if (b->mem) NRCHPM_CUDA(cudaDestroyExternalMemory(b->mem));
+        delete b;
+    });
+}
+int nrchpm_import_external_semaphore(int fd, void** sem_out) {
+    return guard([&] {
+        NRCHPM_REQUIRE(sem_out, "null argument");
+        *sem_out = nullptr;
+        NRCHPM_REQUIRE(fd >= 0, "external semaphore: bad file descriptor");
+        cudaExternalSemaphoreHandleDesc hd{};
+        hd.type = cudaExternalSemaphoreHandleTypeOpaqueFd; hd.handle.fd = fd;
+        cudaExternalSemaphore_t sem = nullptr;
+        NRCHPM_CUDA(cudaImportExternalSemaphore(&sem, &hd));
+        *sem_out = (void*)sem;
+    });
+}
+int nrchpm_release_external_semaphore(void* sem) {
+    return guard([&] { if (sem) NRCHPM_CUDA(cudaDestroyExternalSemaphore((cudaExternalSemaphore_t)sem)); });
+}
+
 int nrc_inference_batch(nrc_cache* c, const float* d_in, float* d_out, uint32_t n, int use_ema, void* stream) {
     return guard([&] { NRCHPM_REQUIRE(c && d_in && d_out, "null argument"); c->impl.inference_set(use_ema, d_in, d_out, n, nullptr, nullptr, (cudaStream_t)stream); });
 }

@@ -42,6 +42,33 @@ def test_python_binding_covers_the_header(built):
     assert l.nrchpm_version() >= 100
 
 
+def test_interop_import_fails_loudly_on_bad_handles(built):
+    """Vulkan interop helpers (reference src/NrcHpmRenderer.cu:644-690, 700-821): no Vulkan device exists here, so only the error paths
+    can run -- a bad descriptor, a zero size, and (with or without a GPU) a descriptor that is not an exported Vulkan allocation must
+    come back as error codes with a message, never as a crash or a mapped pointer."""
+    from nrc_hpm_renderer_b200 import _lib
+    l = _lib.lib()
+    h, p = C.c_void_p(), C.c_void_p()
+    assert l.nrchpm_import_external_buffer(-1, 1024, C.byref(h), C.byref(p)) == _lib.ERR_INVALID and not p.value
+    assert b"file descriptor" in l.nrchpm_last_error()
+    assert l.nrchpm_import_external_buffer(0, 0, C.byref(h), C.byref(p)) == _lib.ERR_INVALID
+    r, w = os.pipe()                                    # a valid descriptor that is not an exported device allocation
+    try:
+        rc = l.nrchpm_import_external_buffer(r, 4096, C.byref(h), C.byref(p))
+        assert rc != 0 and not p.value and not h.value
+        s = C.c_void_p()
+        assert l.nrchpm_import_external_semaphore(-1, C.byref(s)) == _lib.ERR_INVALID
+        rc = l.nrchpm_import_external_semaphore(w, C.byref(s))
+        assert rc != 0 and not s.value
+    finally:
+        for fd in (r, w):
+            try:
+                os.close(fd)
+            except OSError:
+                pass                                    # (a failed import may have consumed it)
+    assert l.nrchpm_release_external_buffer(None) == 0 and l.nrchpm_release_external_semaphore(None) == 0
+
+
 def test_sm100a_code_is_in_the_library(built):
     out = subprocess.run(["cuobjdump", "-lelf", built], capture_output=True, text=True)
     assert "sm_100a" in out.stdout
