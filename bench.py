@@ -306,7 +306,25 @@ def frame_tiles_leg(torch, dist, rank, world, steps, warmup):
     t = torch.tensor([float(np.mean(ms))], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
     out = {"resolution": [Wt, Ht], "tiles": world, "strip_columns": [int(cfg.x_begin), int(cfg.x_end)], "train_records_per_rank_and_step": ta.train_batch_size,
            "ms_per_frame": float(t.item()), "frames_per_s": 1e3 / float(t.item()), "loss": nrc.GetLoss()}
-    r.Destroy(); scene.Destroy(); nrc.Destroy()
+    r.Destroy()
+    if os.environ.get("NRCHPM_TILES_PIPELINED", "1") != "0":
+        # optional mode of the renderer (hpm_render_config.pipeline_train): Train(N) -- here the data-parallel steps with their peer
+        # kernels -- runs on its own stream underneath the tracking passes of frame N + 1; same order of effects, same images.  Frames are
+        # queued back to back (no host synchronisation between them); per-frame time = the main stream from gen_rays to compositing,
+        # which includes waiting for the previous frame's training before Inference(); max over ranks.
+        cfg2 = make_tile_render_config(Wt, Ht, ta, rank, world, pipeline_train=True)
+        r2 = NrcHpmRenderer(Wt, Ht, False, Camera(aspect=Wt / Ht), ta, scene, nrc, render_config=cfg2)
+        ms = []
+        dist.barrier()
+        for i in range(warmup + steps):
+            r2.Render(True, rng.random(4).astype(np.float32))
+            if i >= warmup:
+                ms.append(r2.GetFrameTimeMS())
+        r2.sync()
+        t = torch.tensor([float(np.mean(ms))], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["pipelined_training"] = {"ms_per_frame": float(t.item()), "frames_per_s": 1e3 / float(t.item()), "loss": nrc.GetLoss()}
+        r2.Destroy()
+    scene.Destroy(); nrc.Destroy()
     return out
 
 
