@@ -83,6 +83,12 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
+    def wait_first(self, timeout=3.0):
+        """block until nvidia-smi has printed its first row (a cold box can take a second), so that the load window is never empty"""
+        t_end = time.perf_counter() + timeout
+        while self.proc and not self.rows and time.perf_counter() < t_end and self.proc.poll() is None:
+            time.sleep(0.02)
+
     def begin(self):
         self.t0 = time.perf_counter()
 
@@ -139,7 +145,7 @@ def run_reference(args):
         cmd = [binp, "bench", f"n_infer={N_INFER}", f"batch={TRAIN_BATCH}", f"batches={TRAIN_BATCHES}", f"frames={args.steps}", f"warmup={max(args.warmup, 3)}",
                "pos=0", "dir=0", "depth=6", f"sets={N_SETS}"]
         sampler = ClockSampler(); sampler.start()
-        time.sleep(0.3)                                                  # first nvidia-smi row
+        sampler.wait_first()
         sampler.begin()
         res = subprocess.run(cmd, capture_output=True, text=True)
         sampler.end()
@@ -421,6 +427,8 @@ def run_ours(args):
         sampler.start()                                # rows are only counted inside begin() .. end() below
     for i in range(warmup):
         step(i)
+    if rank == 0:
+        sampler.wait_first()
     barrier()
     launches0 = _lib.lib().nrchpm_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
