@@ -1267,7 +1267,10 @@ void NrcCache::infer_and_train_host(const float* h_in, float* h_out, uint32_t n,
     if (train) { host_tin_.ensure(T * 5); host_tgt_.ensure(T * 3); ensure_train_scratch(B); }
     // 4 chunks for a 1080p frame (8 tiles per resident warpgroup).  Measured alternatives (profiles/r02_e2e_knobs.jsonl): 8 / 16 uniform
     // chunks 1.29 / 1.38 ms, a large first chunk and shrinking later ones (40/25/17/11/7 %) 1.25, two or three chunks 1.27-1.45, against 1.24;
-    // the snapshot the kernels read kept in the persisting part of L2 (access-policy window on these launches): 1.25 against 1.245.
+    // the snapshot the kernels read kept in the persisting part of L2 (access-policy window on these launches): 1.25 against 1.245;
+    // ONE persistent inference launch per frame whose producers wait for per-chunk flags raised behind the H2D copies and whose
+    // consumers count finished tiles for the D2H stream (cuStreamWriteValue32 / cuStreamWaitValue32): 1.235 against 1.25 -- correct in
+    // the parity tests, but 1 % does not pay for an ordering that rests on fences instead of stream events.
     uint32_t chunk = (uint32_t)sm_count_ * 2 * 2 * 8 * kTile;
     if (const char* v = std::getenv("NRCHPM_E2E_CHUNK_TILES")) chunk = (uint32_t)sm_count_ * 2 * 2 * (uint32_t)std::max(1, std::atoi(v)) * kTile;   // experiment knob
     const std::vector<uint32_t> off = uniform_chunks(n, chunk);
