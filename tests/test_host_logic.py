@@ -10,7 +10,7 @@ from nrc_hpm_renderer_b200 import volume
 from nrc_hpm_renderer_b200.config import DEFAULT_ARGV
 from nrc_hpm_renderer_b200.parallel import column_strips
 
-from conftest import golden
+from conftest import ROOT, golden
 
 
 def test_appconfig_default_argv():
@@ -126,3 +126,34 @@ def test_tile_render_configs_partition_frame_and_train_lattice():
     import pytest
     with pytest.raises(ValueError):
         tile_app_config(app, 3)
+
+
+def test_bench_clock_sampler_counts_only_rows_inside_the_load_window():
+    """bench.py's nvidia-smi sampler: rows are stamped on arrival and only those inside [begin(), end()] are reported (the query process
+    is started before the warm-up); throttle reasons are collected from the window only; no process -> an explicit 'unavailable'."""
+    import importlib.util
+    import sys
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    sys.modules["bench_under_test"] = bench
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler(0)
+    assert s.stop()["reasons"] == ["nvidia-smi unavailable"]
+
+    class FakeProc:
+        def terminate(self):
+            pass
+
+        def poll(self):
+            return None
+    s = bench.ClockSampler(0)
+    s.proc = FakeProc()
+    row = lambda sm, cap: [str(sm), "1965", "700.0", "Not Active", "Not Active", "Not Active", cap]
+    s.rows = [(1.0, row(300, "Active")), (2.0, row(1965, "Not Active")), (2.5, row(1950, "Not Active")), (3.0, row(1965, "Not Active")), (9.0, row(210, "Active"))]
+    s.t0, s.t1 = 1.5, 3.5
+    out = s.stop()
+    assert out["samples"] == 3 and out["sm_mhz"] == 1965.0 and out["sm_max_mhz"] == 1965.0 and out["reasons"] == []
+    s.rows.append((3.2, row(1500, "Active")))
+    s.t1 = 3.5
+    out = s.stop()
+    assert out["samples"] == 4 and out["reasons"] == ["sw_power_cap"]
