@@ -92,4 +92,7 @@ def test_nrc_frames_converge_towards_reference():
     both = (ref[..., 1] > 0.5)
     rel_bias = (img[..., 0][both].mean() - ref[..., 0][both].mean()) / ref[..., 0][both].mean()
     print(f"NRC frames after 428 frames of online training at 240x135: rBias {rel_bias:+.4f} against reference/0/0.exr")
-    assert -0.25 <= rel_bias <= 0.10, rel_bias
+    # thesis 5.3.3 reports -0.05 .. -0.08 for the NRC against the path-traced reference (the cache under-estimates slightly); measured here
+    # over repeated runs (the hash-grid gradient is scattered with fp16 atomics, so runs differ): -0.025 .. -0.029.  The band covers
+    # the thesis' figures and ours and nothing with the wrong sign or a double-digit loss of energy (round 1 accepted -0.25 .. +0.10).
+    assert -0.10 <= rel_bias <= 0.02, rel_bias
